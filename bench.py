@@ -1,0 +1,317 @@
+#!/usr/bin/env python
+"""bench.py -- DPC-RNN training-step throughput on B200 (BASELINE.json metric: clips/sec, device-timed).
+
+    python bench.py --gpus 1 --steps K --warmup W                 # this repo's CUDA path
+    torchrun --nproc-per-node N ... bench.py --gpus N ...         # one rank per GPU, NCCL grad all-reduce
+    python bench.py --impl reference ...                          # the reference algorithm on host cores (oracle port)
+
+One "step" = forward + fused NCE loss + backward + gradient all-reduce + Adam over one batch of
+synthetic video ([B,8,3,5,img,img] fp32, B clips per GPU; BASELINE config 2: 2d3d-R18, 128^2, B=128).
+Prints ONE JSON line (rank 0).  See DESIGN.md §Measurement for every field.
+"""
+import argparse
+import contextlib
+import io
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = 'clips/sec (device-timed) DPC-RNN 2d3d-R18 128^2 train step'
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=8)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--net', default='resnet18')
+    ap.add_argument('--img_dim', type=int, default=128)
+    ap.add_argument('--batch_size', type=int, default=128, help='clips per GPU')
+    ap.add_argument('--pred_step', type=int, default=3)
+    ap.add_argument('--no_cpu_baseline', action='store_true')
+    ap.add_argument('--no_e2e', action='store_true')
+    return ap.parse_args()
+
+
+def workload(a, n):
+    return {'workload': 'DPC-RNN train step (fwd + NCE loss + bwd + grad all-reduce + Adam), 2d3d-%s, img %d, '
+                        'num_seq 8, seq_len 5, pred_step %d, batch %d clips/GPU, synthetic video'
+                        % (a.net.replace('resnet', 'R'), a.img_dim, a.pred_step, a.batch_size),
+            'network': a.net, 'img_dim': a.img_dim, 'batch_per_gpu': a.batch_size,
+            'global_batch': a.batch_size * n, 'parallelism': 'dp%d' % n,
+            'l2': 'input batch %.2f GB/step per GPU > 126 MB L2 (no explicit flush needed)'
+                  % (a.batch_size * 8 * 3 * 5 * a.img_dim ** 2 * 4 / 1e9)}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d.get('hbm_gbs', 6650.0), d.get('bf16_tflops_sustained', 1400.0), 'measured'
+    return 6650.0, 1590.0, 'fallback'
+
+
+# ---------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region"""
+    Q = ('clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+         'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index):
+        self.lines, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(index), '--query-gpu=' + self.Q,
+                                          '--format=csv,noheader,nounits', '-lms', '200'],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return None
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(',')]
+            if len(f) < 6:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for nme, v in zip(names, f[2:6]):
+                if v == 'Active':
+                    reasons.add(nme)
+        if not sm:
+            return None
+        sm.sort()
+        return {'sm_mhz': sm[len(sm) // 2], 'sm_max_mhz': max(mx), 'reasons': sorted(reasons), 'samples': len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------
+def run_reference(a, rank, world):
+    """the reference's algorithm on the host cores: the oracle port (oracle/dpc_oracle.py; the
+    reference itself is Python over ATen and cannot travel to the GPU box).  Bounded sample: B=4
+    clips per step (BASELINE config 1)."""
+    if rank != 0:
+        return
+    import torch
+    from oracle import dpc_oracle as O
+    torch.set_num_threads(os.cpu_count() or 1)
+    bs = 4
+    t = O.cpu_train_step_time(a.net, a.img_dim, batch=bs, steps=max(1, a.steps), warmup=max(1, min(a.warmup, 2)))
+    v = bs / t
+    cfg = workload(a, world)
+    line = {'impl': 'reference', 'metric': METRIC, 'value': v, 'unit': 'clips/s', 'n_gpus': a.gpus,
+            'steps': a.steps, 'warmup': a.warmup, 'ms_per_step': t * 1e3, 'higher_is_better': True,
+            'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic', 'config': cfg,
+            'cpu_baseline': {'value': v, 'unit': 'clips/s', 'cores': torch.get_num_threads(), 'kind': 'port',
+                             'sample': 'median of %d train steps (fwd+CE+bwd+Adam) at batch %d clips, %s img %d, '
+                                       'torch CPU fp32' % (max(1, a.steps), bs, a.net, a.img_dim)},
+            'e2e': {'value': v, 'unit': 'clips/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+            'gpu_launches': 0}
+    print(json.dumps(line))
+
+
+def conv_family_flops(network, NB, T, H, W):
+    """algorithmic FLOPs (2*MAC) of the im2col-GEMM conv family per step: fwd + dgrad + wgrad"""
+    from dpc_b200.arch import backbone_spec
+    from dpc_b200.engine import _out_extent as e
+    Hc, Wc = e(e(H, 7, 2, 3), 3, 2, 1), e(e(W, 7, 2, 3), 3, 2, 1)
+    Tc = T
+    total = 0
+    for b in backbone_spec(network):
+        k = (3, 3, 3) if b['is3d'] else (1, 3, 3)
+        s = (b['stride'],) * 3 if b['is3d'] else (1, b['stride'], b['stride'])
+        p = (1, 1, 1) if b['is3d'] else (0, 1, 1)
+        To, Ho, Wo = e(Tc, k[0], s[0], p[0]), e(Hc, k[1], s[1], p[1]), e(Wc, k[2], s[2], p[2])
+        rows = NB * To * Ho * Wo
+        taps = k[0] * k[1] * k[2]
+        total += 2 * rows * b['planes'] * taps * b['inplanes']           # conv1
+        total += 2 * rows * b['planes'] * taps * b['planes']             # conv2
+        if b['downsample']:
+            total += 2 * rows * b['planes'] * b['inplanes']
+        Tc, Hc, Wc = To, Ho, Wo
+    return 3 * total
+
+
+def run_b200(a, rank, local_rank, world):
+    import torch
+    import torch.distributed as dist
+    import dpc_b200
+    from dpc_b200 import engine
+    torch.cuda.set_device(local_rank)
+    dev = torch.device('cuda', local_rank)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+    torch.manual_seed(0)
+    with contextlib.redirect_stdout(io.StringIO()):
+        model = dpc_b200.DPC_RNN(a.img_dim, num_seq=8, seq_len=5, pred_step=a.pred_step, network=a.net)
+    model = model.to(dev).train()                                    # dropout on, as in training
+    crit = dpc_b200.NCECriterion()
+    trainer = dpc_b200.FlatTrainer(model, lr=1e-3, weight_decay=1e-5)
+    B = a.batch_size
+    shape = (B, 8, 3, 5, a.img_dim, a.img_dim)
+    g = torch.Generator().manual_seed(1234 + rank)
+    host = [torch.randn(shape, generator=g).pin_memory() for _ in range(2)]
+    x_dev = host[0].to(dev)
+    L = dpc_b200.lib()
+
+    def step(x):
+        trainer.zero_grad()
+        score, _ = model(x)
+        loss = crit(score)
+        loss.backward()
+        trainer.step()
+        return loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if world > 1:
+            t = torch.tensor([ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t[0])
+        return ms
+
+    # ---- device-resident ("value") -------------------------------------------------------------
+    for _ in range(a.warmup):
+        step(x_dev)
+    barrier()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    n0 = L.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(a.steps):
+        loss = step(x_dev)
+    e1.record()
+    barrier()
+    ms_total = max_over_ranks(e0.elapsed_time(e1))
+    launches = L.launch_count() - n0
+    clocks = sampler.stop() if sampler else None
+    ms_step = ms_total / a.steps
+    value = world * B / (ms_step / 1e3)
+    last_loss = float(loss)
+
+    # ---- end to end: pinned host input -> H2D (prefetched on a copy stream) -> step -> loss.item() ----
+    e2e = None
+    if not a.no_e2e:
+        copy_stream = torch.cuda.Stream()
+        bufs = [torch.empty(shape, device=dev) for _ in range(2)]
+        ready = [torch.cuda.Event() for _ in range(2)]
+        free = [torch.cuda.Event() for _ in range(2)]
+
+        def prefetch(i):
+            j = i % 2
+            with torch.cuda.stream(copy_stream):
+                copy_stream.wait_event(free[j])
+                bufs[j].copy_(host[j], non_blocking=True)
+                ready[j].record(copy_stream)
+
+        for j in range(2):
+            free[j].record()
+        barrier()
+        nwarm = 1
+        prefetch(0)
+        t0 = None
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        for i in range(nwarm + a.steps):
+            if i == nwarm:
+                barrier()
+                ev0.record()
+                t0 = time.perf_counter()
+            prefetch(i + 1)
+            torch.cuda.current_stream().wait_event(ready[i % 2])
+            loss = step(bufs[i % 2])
+            free[i % 2].record()
+            _ = loss.item()                                          # the D2H read of the step's result
+        ev1.record()
+        barrier()
+        wall = (time.perf_counter() - t0) * 1e3
+        ms_e2e = max_over_ranks(max(ev0.elapsed_time(ev1), 0.0)) / a.steps
+        e2e = {'value': world * B / (ms_e2e / 1e3), 'unit': 'clips/s',
+               'h2d_bytes_per_step': host[0].numel() * 4, 'd2h_bytes_per_step': 4,
+               'ms_per_step': ms_e2e, 'wall_ms_per_step': wall / a.steps}
+
+    # ---- roofline of the dominant kernel family (one extra, instrumented step) -------------------
+    roof = None
+    fam = None
+    if rank == 0:
+        timer = engine.EventTimer()
+        engine.set_timer(timer)
+        step(x_dev)
+        engine.set_timer(None)
+        tot = timer.totals()
+        fam = {k: {'calls': c, 'ms': round(t, 3)} for k, (c, t) in sorted(tot.items(), key=lambda kv: -kv[1][1])}
+        conv_ms = sum(t for k, (c, t) in tot.items() if k in ('conv_fwd', 'conv_dgrad', 'conv_wgrad'))
+        flops = conv_family_flops(a.net, B * 8, 5, a.img_dim, a.img_dim)
+        hbm, tf, how = measured_peaks()
+        ach = flops / (conv_ms / 1e3) / 1e12
+        roof = {'kernel': 'conv3d implicit-GEMM family (fwd+dgrad+wgrad, all layers)', 'bound': 'tensor',
+                'achieved': ach, 'peak': tf, 'unit': 'TFLOP/s', 'frac': ach / tf, 'traffic': None,
+                'peak_source': how + ' bf16_tflops_sustained', 'algorithmic_flops_per_step': flops,
+                'family_ms_per_step': conv_ms, 'share_of_step': conv_ms / ms_step}
+    else:
+        step(x_dev)                                                  # keep the collective count equal
+    barrier()
+
+    cpu = None
+    if rank == 0 and world == 1 and not a.no_cpu_baseline:
+        from oracle import dpc_oracle as O
+        torch.set_num_threads(os.cpu_count() or 1)
+        bs = 4
+        t = O.cpu_train_step_time(a.net, a.img_dim, batch=bs, steps=5, warmup=1)
+        cpu = {'value': bs / t, 'unit': 'clips/s', 'cores': torch.get_num_threads(), 'kind': 'port',
+               'sample': 'median of 5 train steps (fwd+CE+bwd+Adam) at batch %d clips (BASELINE config 1), '
+                         'torch CPU fp32 oracle port' % bs}
+
+    if rank == 0:
+        line = {'metric': METRIC, 'value': value, 'unit': 'clips/s', 'n_gpus': world, 'steps': a.steps,
+                'warmup': a.warmup, 'ms_per_step': ms_step, 'higher_is_better': True, 'scaling': 'weak',
+                'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic', 'config': workload(a, world),
+                'clocks': clocks, 'e2e': e2e, 'gpu_launches': int(launches), 'roofline': roof,
+                'cpu_baseline': cpu, 'kernel_families_ms': fam, 'loss': last_loss}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    a = parse()
+    rank = int(os.environ.get('RANK', 0))
+    local_rank = int(os.environ.get('LOCAL_RANK', 0))
+    world = int(os.environ.get('WORLD_SIZE', 1))
+    if a.impl == 'reference':
+        return run_reference(a, rank, world)
+    if world != a.gpus:
+        if a.gpus > 1 and world == 1:
+            sys.exit('bench.py --gpus %d must be launched with torchrun --nproc-per-node %d' % (a.gpus, a.gpus))
+    os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+    run_b200(a, rank, local_rank, world)
+
+
+if __name__ == '__main__':
+    main()

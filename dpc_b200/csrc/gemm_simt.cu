@@ -1,0 +1,172 @@
+// Generic fp32 CUDA-core GEMM with arbitrary transposes / leading dimensions.
+// Used for the small, latency-bound GEMMs of the ConvGRU / predictor (convrnn.py:29-33,
+// model_3d.py:36-40,68) and as the exact-fp32 fallback shape for the score matmul.
+#include "common.cuh"
+
+namespace {
+
+constexpr int TM = 64, TN = 64, TK = 16;
+
+template <bool TA, bool TB>
+__global__ void __launch_bounds__(256) gemm_f32_kernel(int M, int N, int K, float alpha,
+                                                        const float* __restrict__ A, int lda,
+                                                        const float* __restrict__ B, int ldb,
+                                                        float beta, float* __restrict__ C, int ldc) {
+    __shared__ float As[TK][TM + 4];
+    __shared__ float Bs[TK][TN + 4];
+    const int tid = threadIdx.x;
+    const int m0 = blockIdx.y * TM, n0 = blockIdx.x * TN;
+    const int tm = (tid / 16) * 4, tn = (tid % 16) * 4;
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+    for (int k0 = 0; k0 < K; k0 += TK) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            int idx = tid + e * 256;
+            int m, k;
+            if (TA) { k = idx / TM; m = idx % TM; } else { m = idx / TK; k = idx % TK; }
+            int gm = m0 + m, gk = k0 + k;
+            float v = 0.f;
+            if (gm < M && gk < K) v = TA ? A[(size_t)gk * lda + gm] : A[(size_t)gm * lda + gk];
+            As[k][m] = v;
+        }
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            int idx = tid + e * 256;
+            int n, k;
+            if (TB) { n = idx / TK; k = idx % TK; } else { k = idx / TN; n = idx % TN; }
+            int gn = n0 + n, gk = k0 + k;
+            float v = 0.f;
+            if (gn < N && gk < K) v = TB ? B[(size_t)gn * ldb + gk] : B[(size_t)gk * ldb + gn];
+            Bs[k][n] = v;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < TK; ++k) {
+            float4 a = *reinterpret_cast<const float4*>(&As[k][tm]);
+            float4 b = *reinterpret_cast<const float4*>(&Bs[k][tn]);
+            float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        int gm = m0 + tm + i;
+        if (gm >= M) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            int gn = n0 + tn + j;
+            if (gn >= N) continue;
+            float* c = &C[(size_t)gm * ldc + gn];
+            float v = alpha * acc[i][j];
+            if (beta != 0.f) v += beta * (*c);
+            *c = v;
+        }
+    }
+}
+
+__global__ void gather_rows_kernel(const float4* __restrict__ src, float4* __restrict__ dst,
+                                   long long rows, int D4, long long inner, long long outer,
+                                   long long offset) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    long long total = rows * D4;
+    for (; i < total; i += (long long)gridDim.x * blockDim.x) {
+        long long r = i / D4;
+        int c = (int)(i % D4);
+        long long sr = (r / inner) * outer + offset + r % inner;
+        dst[i] = src[sr * D4 + c];
+    }
+}
+
+__global__ void scatter_rows_kernel(const float4* __restrict__ src, float4* __restrict__ dst,
+                                    long long rows, int D4, long long inner, long long outer,
+                                    long long offset, int accumulate) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    long long total = rows * D4;
+    for (; i < total; i += (long long)gridDim.x * blockDim.x) {
+        long long r = i / D4;
+        int c = (int)(i % D4);
+        long long dr = (r / inner) * outer + offset + r % inner;
+        float4 v = src[i];
+        if (accumulate) {
+            float4 o = dst[dr * D4 + c];
+            v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
+        }
+        dst[dr * D4 + c] = v;
+    }
+}
+
+// colsum: grid.x over column groups of 32, each block reduces all rows for 32 columns.
+__global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ A, long long rows, int N,
+                                                      float* __restrict__ out, int accumulate) {
+    __shared__ float red[8][33];
+    int col = blockIdx.x * 32 + (threadIdx.x & 31);
+    int rl = threadIdx.x >> 5;
+    float s = 0.f;
+    if (col < N)
+        for (long long r = rl; r < rows; r += 8) s += A[r * N + col];
+    red[rl][threadIdx.x & 31] = s;
+    __syncthreads();
+    if (rl == 0 && col < N) {
+        float t = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) t += red[i][threadIdx.x & 31];
+        out[col] = accumulate ? out[col] + t : t;
+    }
+}
+
+}  // namespace
+
+extern "C" int dpc_gemm_f32(int transA, int transB, int M, int N, int K, float alpha, const float* A,
+                            int lda, const float* B, int ldb, float beta, float* C, int ldc,
+                            void* stream) {
+    DPC_REQUIRE(M > 0 && N > 0 && K > 0, "dpc_gemm_f32: bad dims %d %d %d", M, N, K);
+    DPC_REQUIRE(A && B && C, "dpc_gemm_f32: null pointer");
+    dim3 grid(ceil_div(N, TN), ceil_div(M, TM));
+    cudaStream_t st = as_stream(stream);
+    if (!transA && !transB) gemm_f32_kernel<false, false><<<grid, 256, 0, st>>>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc);
+    else if (!transA && transB) gemm_f32_kernel<false, true><<<grid, 256, 0, st>>>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc);
+    else if (transA && !transB) gemm_f32_kernel<true, false><<<grid, 256, 0, st>>>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc);
+    else gemm_f32_kernel<true, true><<<grid, 256, 0, st>>>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc);
+    DPC_LAUNCH_CHECK();
+    return DPC_OK;
+}
+
+extern "C" int dpc_gather_rows(const float* src, float* dst, int64_t rows, int D, int64_t inner,
+                               int64_t outer, int64_t offset, void* stream) {
+    DPC_REQUIRE(D % 4 == 0 && rows > 0 && inner > 0, "dpc_gather_rows: bad args");
+    long long total = rows * (D / 4);
+    int blocks = (int)((total + 255) / 256);
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    gather_rows_kernel<<<blocks, 256, 0, as_stream(stream)>>>((const float4*)src, (float4*)dst, rows, D / 4,
+                                                             inner, outer, offset);
+    DPC_LAUNCH_CHECK();
+    return DPC_OK;
+}
+
+extern "C" int dpc_scatter_rows(const float* src, float* dst, int64_t rows, int D, int64_t inner,
+                                int64_t outer, int64_t offset, int accumulate, void* stream) {
+    DPC_REQUIRE(D % 4 == 0 && rows > 0 && inner > 0, "dpc_scatter_rows: bad args");
+    long long total = rows * (D / 4);
+    int blocks = (int)((total + 255) / 256);
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    scatter_rows_kernel<<<blocks, 256, 0, as_stream(stream)>>>((const float4*)src, (float4*)dst, rows, D / 4,
+                                                              inner, outer, offset, accumulate);
+    DPC_LAUNCH_CHECK();
+    return DPC_OK;
+}
+
+extern "C" int dpc_colsum(const float* A, int64_t rows, int N, float* out, int accumulate, void* stream) {
+    DPC_REQUIRE(rows > 0 && N > 0, "dpc_colsum: bad args");
+    colsum_kernel<<<ceil_div(N, 32), 256, 0, as_stream(stream)>>>(A, rows, N, out, accumulate);
+    DPC_LAUNCH_CHECK();
+    return DPC_OK;
+}

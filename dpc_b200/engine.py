@@ -1,0 +1,506 @@
+"""Host-side orchestration of the DPC-RNN hot path over the C ABI (include/dpc_b200.h).
+
+Two stages, each a forward/backward pair driven from a torch.autograd.Function
+(dpc_b200/resnet_2d3d.py, dpc_b200/model_3d.py):
+
+  backbone : ResNet2d3d_full.forward            (/root/reference/backbone/resnet_2d3d.py:259-270)
+  head     : avg-pool/ReLU split, ConvGRU, predictor loop, score matmul
+             (/root/reference/dpc/model_3d.py:53-83, backbone/convrnn.py:24-34,62-88)
+
+Data layout in HBM: activations are channels-last rows [NB*T*H*W, C] fp32; the caller's NCDHW
+video block is read directly by the stem kernel.  PyTorch provides memory (caching allocator) and
+the current stream only; every FLOP below is issued through libdpc_b200.so.
+"""
+import math
+
+import torch
+
+from ._lib import lib, ptr, ConvGeom
+from .arch import backbone_spec, FEATURE_SIZE
+
+BN_EPS = 1e-5
+
+# optional per-kernel-family device timer (bench.py's roofline leg); None on the normal path
+_TIMER = None
+
+
+def set_timer(timer):
+    """timer: None or an object with .start(tag) -> token and .stop(token) using CUDA events"""
+    global _TIMER
+    _TIMER = timer
+
+
+class EventTimer:
+    """CUDA-event timer on the current stream; .totals() -> {tag: (calls, ms)} after a synchronize"""
+
+    def __init__(self):
+        self.records = []
+
+    def start(self, tag):
+        a = torch.cuda.Event(enable_timing=True)
+        b = torch.cuda.Event(enable_timing=True)
+        a.record()
+        return (tag, a, b)
+
+    def stop(self, tok):
+        tok[2].record()
+        self.records.append(tok)
+
+    def totals(self):
+        torch.cuda.synchronize()
+        out = {}
+        for tag, a, b in self.records:
+            c, t = out.get(tag, (0, 0.0))
+            out[tag] = (c + 1, t + a.elapsed_time(b))
+        return out
+
+
+def _timed(tag):
+    def deco(fn):
+        def wrapped(*a, **k):
+            if _TIMER is None:
+                return fn(*a, **k)
+            tok = _TIMER.start(tag)
+            try:
+                return fn(*a, **k)
+            finally:
+                _TIMER.stop(tok)
+        return wrapped
+    return deco
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _empty(shape, ref, dtype=torch.float32):
+    return torch.empty(shape, dtype=dtype, device=ref.device)
+
+
+def _out_extent(i, k, s, p):
+    return (i + 2 * p - k) // s + 1
+
+
+class ConvSite:
+    """geometry + packed weights of one Conv3d call site"""
+    __slots__ = ('geom', 'taps', 'Ci', 'Co', 'rows_in', 'rows_out', 'dims_out', 'wf', 'wd')
+
+    def __init__(self, NB, dims_in, Ci, Co, k, s, p):
+        Ti, Hi, Wi = dims_in
+        To, Ho, Wo = (_out_extent(Ti, k[0], s[0], p[0]), _out_extent(Hi, k[1], s[1], p[1]),
+                      _out_extent(Wi, k[2], s[2], p[2]))
+        self.geom = ConvGeom(NB, Ti, Hi, Wi, Ci, To, Ho, Wo, Co, k[0], k[1], k[2], s[0], s[1], s[2],
+                             p[0], p[1], p[2])
+        self.taps = k[0] * k[1] * k[2]
+        self.Ci, self.Co = Ci, Co
+        self.rows_in = NB * Ti * Hi * Wi
+        self.rows_out = NB * To * Ho * Wo
+        self.dims_out = (To, Ho, Wo)
+        self.wf = self.wd = None
+
+    def pack(self, w, st):
+        L = lib()
+        self.wf = _empty((self.taps, self.Ci, self.Co), w)
+        self.wd = _empty((self.taps, self.Co, self.Ci), w)
+        L.pack_conv_weight(ptr(w), ptr(self.wf), ptr(self.wd), self.Co, self.Ci, self.taps, st)
+
+    @_timed('conv_fwd')
+    def fwd(self, x, st):
+        y = _empty((self.rows_out, self.Co), x)
+        lib().conv3d_fwd(self.geom, ptr(x), ptr(self.wf), ptr(y), st)
+        return y
+
+    @_timed('conv_dgrad')
+    def dgrad(self, dy, st, dx=None):
+        acc = 1
+        if dx is None:
+            dx = _empty((self.rows_in, self.Ci), dy)
+            acc = 0
+        lib().conv3d_dgrad(self.geom, ptr(dy), ptr(self.wd), ptr(dx), acc, st)
+        return dx
+
+    @_timed('conv_wgrad')
+    def wgrad(self, x, dy, st):
+        """returns dW in the parameter layout [Co,Ci,kT,kH,kW]"""
+        L = lib()
+        dwp = _empty((self.taps, self.Ci, self.Co), x)
+        L.conv3d_wgrad(self.geom, ptr(x), ptr(dy), ptr(dwp), st)
+        g = self.geom
+        dw = _empty((self.Co, self.Ci, g.kT, g.kH, g.kW), x)
+        L.unpack_conv_wgrad(ptr(dwp), ptr(dw), self.Co, self.Ci, self.taps, st)
+        return dw
+
+
+@_timed('bn_stats')
+def _bn_stats(y, rows, C, st):
+    ws = torch.empty(2 * C, dtype=torch.float64, device=y.device)
+    mean = _empty((C,), y)
+    rstd = _empty((C,), y)
+    lib().bn_stats(ptr(y), rows, C, ptr(ws), ptr(mean), ptr(rstd), BN_EPS, st)
+    return mean, rstd
+
+
+@_timed('bn_apply')
+def _bn_apply(y, mean, rstd, gamma, beta, relu, rows, C, st, res=None, rbn=None):
+    out = torch.empty_like(y)
+    r = rbn if rbn is not None else (None, None, None, None)
+    lib().bn_apply_fwd(ptr(y), ptr(mean), ptr(rstd), ptr(gamma), ptr(beta), ptr(res), ptr(r[0]), ptr(r[1]),
+                       ptr(r[2]), ptr(r[3]), 1 if relu else 0, ptr(out), rows, C, st)
+    return out
+
+
+@_timed('bn_bwd')
+def _bn_bwd(dout, out, relu, y, mean, rstd, gamma, rows, C, st, want_g=False):
+    ws = torch.empty(2 * C, dtype=torch.float64, device=y.device)
+    dgamma = _empty((C,), y)
+    dbeta = _empty((C,), y)
+    dy = torch.empty_like(y)
+    g = torch.empty_like(y) if want_g else None
+    lib().bn_bwd(ptr(dout), ptr(out), 1 if relu else 0, ptr(y), ptr(mean), ptr(rstd), ptr(gamma), ptr(ws),
+                 ptr(dgamma), ptr(dbeta), ptr(dy), ptr(g), rows, C, st)
+    return dy, dgamma, dbeta, g
+
+
+# ==================================================================================================
+# backbone
+# ==================================================================================================
+def backbone_param_names(network):
+    names = ['conv1.weight', 'bn1.weight', 'bn1.bias']
+    for b in backbone_spec(network):
+        p = b['name']
+        names += [p + '.conv1.weight', p + '.bn1.weight', p + '.bn1.bias',
+                  p + '.conv2.weight', p + '.bn2.weight', p + '.bn2.bias']
+        if b['downsample']:
+            names += [p + '.downsample.0.weight', p + '.downsample.1.weight', p + '.downsample.1.bias']
+    return names
+
+
+def backbone_forward(network, x, P, need_ctx=True):
+    """x [NB,3,T,H,W] fp32 contiguous CUDA; P: name -> tensor.  Returns (feature rows [NB*To*Ho*Wo, 256],
+    (To,Ho,Wo), ctx)."""
+    L = lib()
+    st = _stream()
+    NB, Cin, T, H, W = x.shape
+    if Cin != 3:
+        raise ValueError('backbone expects 3 input channels, got %d' % Cin)
+    Ho, Wo = _out_extent(H, 7, 2, 3), _out_extent(W, 7, 2, 3)
+    rows0 = NB * T * Ho * Wo
+    y0 = _empty((rows0, 64), x)
+    _timed('stem_fwd')(L.stem_conv_fwd)(ptr(x), ptr(P['conv1.weight']), ptr(y0), NB, T, H, W, st)
+    m0, r0 = _bn_stats(y0, rows0, 64, st)
+    Hp, Wp = _out_extent(Ho, 3, 2, 1), _out_extent(Wo, 3, 2, 1)
+    a0 = _empty((NB * T * Hp * Wp, 64), x)
+    _timed('stem_pool_fwd')(L.bn_relu_maxpool_fwd)(ptr(y0), ptr(m0), ptr(r0), ptr(P['bn1.weight']), ptr(P['bn1.bias']), ptr(a0),
+                          NB * T, Ho, Wo, 64, st)
+    ctx = dict(network=network, x=x, y0=y0, m0=m0, r0=r0, a0=a0, stem_dims=(NB, T, H, W, Ho, Wo), blocks=[])
+    cur, dims, C = a0, (T, Hp, Wp), 64
+    for b in backbone_spec(network):
+        p = b['name']
+        if b['is3d']:
+            k, pad = (3, 3, 3), (1, 1, 1)
+            s1 = (b['stride'],) * 3
+        else:
+            k, pad = (1, 3, 3), (0, 1, 1)
+            s1 = (1, b['stride'], b['stride'])
+        c1 = ConvSite(NB, dims, b['inplanes'], b['planes'], k, s1, pad)
+        c1.pack(P[p + '.conv1.weight'], st)
+        y1 = c1.fwd(cur, st)
+        m1, r1 = _bn_stats(y1, c1.rows_out, c1.Co, st)
+        a1 = _bn_apply(y1, m1, r1, P[p + '.bn1.weight'], P[p + '.bn1.bias'], True, c1.rows_out, c1.Co, st)
+        c2 = ConvSite(NB, c1.dims_out, b['planes'], b['planes'], k, (1, 1, 1), pad)
+        c2.pack(P[p + '.conv2.weight'], st)
+        y2 = c2.fwd(a1, st)
+        m2, r2 = _bn_stats(y2, c2.rows_out, c2.Co, st)
+        rec = dict(spec=b, c1=c1, c2=c2, xin=cur, y1=y1, m1=m1, r1=r1, a1=a1, y2=y2, m2=m2, r2=r2)
+        if b['downsample']:
+            cd = ConvSite(NB, dims, b['inplanes'], b['planes'], (1, 1, 1), s1, (0, 0, 0))
+            cd.pack(P[p + '.downsample.0.weight'], st)
+            yd = cd.fwd(cur, st)
+            md, rd = _bn_stats(yd, cd.rows_out, cd.Co, st)
+            out = _bn_apply(y2, m2, r2, P[p + '.bn2.weight'], P[p + '.bn2.bias'], b['final_relu'],
+                            c2.rows_out, c2.Co, st, res=yd,
+                            rbn=(md, rd, P[p + '.downsample.1.weight'], P[p + '.downsample.1.bias']))
+            rec.update(cd=cd, yd=yd, md=md, rd=rd)
+        else:
+            out = _bn_apply(y2, m2, r2, P[p + '.bn2.weight'], P[p + '.bn2.bias'], b['final_relu'],
+                            c2.rows_out, c2.Co, st, res=cur)
+        rec['out'] = out
+        if need_ctx:
+            ctx['blocks'].append(rec)
+        cur, dims, C = out, c2.dims_out, b['planes']
+    return cur, dims, (ctx if need_ctx else None)
+
+
+def backbone_backward(ctx, dout, P):
+    """dout: rows [NB*To*Ho*Wo, 256].  Returns dict name -> grad (parameter layouts)."""
+    L = lib()
+    st = _stream()
+    G = {}
+    for rec in reversed(ctx['blocks']):
+        b = rec['spec']
+        p = b['name']
+        c1, c2 = rec['c1'], rec['c2']
+        relu = b['final_relu']
+        has_ds = b['downsample']
+        dy2, G[p + '.bn2.weight'], G[p + '.bn2.bias'], g = _bn_bwd(
+            dout, rec['out'], relu, rec['y2'], rec['m2'], rec['r2'], P[p + '.bn2.weight'],
+            c2.rows_out, c2.Co, st, want_g=not has_ds)
+        if has_ds:
+            cd = rec['cd']
+            dyd, G[p + '.downsample.1.weight'], G[p + '.downsample.1.bias'], _ = _bn_bwd(
+                dout, rec['out'], relu, rec['yd'], rec['md'], rec['rd'], P[p + '.downsample.1.weight'],
+                cd.rows_out, cd.Co, st)
+        del dout
+        G[p + '.conv2.weight'] = c2.wgrad(rec['a1'], dy2, st)
+        da1 = c2.dgrad(dy2, st)
+        del dy2
+        dy1, G[p + '.bn1.weight'], G[p + '.bn1.bias'], _ = _bn_bwd(
+            da1, rec['a1'], True, rec['y1'], rec['m1'], rec['r1'], P[p + '.bn1.weight'],
+            c1.rows_out, c1.Co, st)
+        del da1
+        G[p + '.conv1.weight'] = c1.wgrad(rec['xin'], dy1, st)
+        if has_ds:
+            dx = c1.dgrad(dy1, st)
+            cd.dgrad(dyd, st, dx=dx)
+            G[p + '.downsample.0.weight'] = cd.wgrad(rec['xin'], dyd, st)
+            del dyd
+        else:
+            dx = c1.dgrad(dy1, st, dx=g)          # dx = g + dgrad
+        del dy1
+        dout = dx
+        rec.clear()
+    NB, T, H, W, Ho, Wo = ctx['stem_dims']
+    rows0 = NB * T * Ho * Wo
+    g0 = torch.empty_like(ctx['y0'])
+    _timed('stem_pool_bwd')(L.bn_relu_maxpool_bwd)(ptr(ctx['y0']), ptr(ctx['m0']), ptr(ctx['r0']), ptr(P['bn1.weight']),
+                          ptr(P['bn1.bias']), ptr(ctx['a0']), ptr(dout), ptr(g0), NB * T, Ho, Wo, 64, st)
+    del dout
+    dy0, G['bn1.weight'], G['bn1.bias'], _ = _bn_bwd(g0, None, False, ctx['y0'], ctx['m0'], ctx['r0'],
+                                                    P['bn1.weight'], rows0, 64, st)
+    del g0
+    dw0 = torch.empty_like(P['conv1.weight'])
+    _timed('stem_wgrad')(L.stem_conv_wgrad)(ptr(ctx['x']), ptr(dy0), ptr(dw0), NB, T, H, W, st)
+    G['conv1.weight'] = dw0
+    return G
+
+
+# ==================================================================================================
+# head: pool/split + ConvGRU + predictor + score
+# ==================================================================================================
+HEAD_PARAM_NAMES = ['agg.cell_list.0.reset_gate.weight', 'agg.cell_list.0.reset_gate.bias',
+                    'agg.cell_list.0.update_gate.weight', 'agg.cell_list.0.update_gate.bias',
+                    'agg.cell_list.0.out_gate.weight', 'agg.cell_list.0.out_gate.bias',
+                    'network_pred.0.weight', 'network_pred.0.bias',
+                    'network_pred.2.weight', 'network_pred.2.bias']
+
+
+def _gemm(ta, tb, M, N, K, A, lda, B, ldb, C, ldc, st, beta=0.0, a_off=0, b_off=0, c_off=0):
+    es = 4
+    lib().gemm_f32(ta, tb, M, N, K, 1.0, A.data_ptr() + a_off * es, lda, B.data_ptr() + b_off * es, ldb,
+                   beta, C.data_ptr() + c_off * es, ldc, st)
+
+
+class _Gru:
+    """one ConvGRU cell with kernel_size 1, acting on [R, D] row matrices"""
+
+    def __init__(self, P, D, st):
+        self.Wr, self.br = P['agg.cell_list.0.reset_gate.weight'], P['agg.cell_list.0.reset_gate.bias']
+        self.Wz, self.bz = P['agg.cell_list.0.update_gate.weight'], P['agg.cell_list.0.update_gate.bias']
+        self.Wo, self.bo = P['agg.cell_list.0.out_gate.weight'], P['agg.cell_list.0.out_gate.bias']
+        self.D, self.st = D, st
+
+    def xproj(self, X, rows):
+        """XP [rows, 3D] = X @ [Wx_z | Wx_r | Wx_o]^T   (x-part of the concatenated input, columns 0..D)"""
+        D = self.D
+        XP = _empty((rows, 3 * D), X)
+        for gi, Wg in enumerate((self.Wz, self.Wr, self.Wo)):
+            _gemm(0, 1, rows, D, D, X, D, Wg, 2 * D, XP, 3 * D, self.st, c_off=gi * D)
+        return XP
+
+    def step(self, XP, xp_row0, h, R, p, seed, offset):
+        """XP rows [xp_row0, xp_row0+R) hold this step's x projections.  Returns (h_new, saved)."""
+        L, D, st = lib(), self.D, self.st
+        hzr = _empty((R, 2 * D), h)
+        _gemm(0, 1, R, D, D, h, D, self.Wz, 2 * D, hzr, 2 * D, st, b_off=D)
+        _gemm(0, 1, R, D, D, h, D, self.Wr, 2 * D, hzr, 2 * D, st, b_off=D, c_off=D)
+        z, r, hr = torch.empty_like(h), torch.empty_like(h), torch.empty_like(h)
+        base = XP.data_ptr() + xp_row0 * 3 * D * 4
+        L.gru_gates_zr(base, base + D * 4, 3 * D, ptr(hzr), ptr(self.bz), ptr(self.br), ptr(h), ptr(z), ptr(r),
+                       ptr(hr), R, D, st)
+        ho = torch.empty_like(h)
+        _gemm(0, 1, R, D, D, hr, D, self.Wo, 2 * D, ho, D, st, b_off=D)
+        o, hn = torch.empty_like(h), torch.empty_like(h)
+        keep = torch.empty_like(h) if p > 0 else None
+        L.gru_out(base + 2 * D * 4, 3 * D, ptr(ho), ptr(self.bo), ptr(h), ptr(z), ptr(o), ptr(hn), ptr(keep),
+                  float(p), seed, offset, R, D, st)
+        return hn, dict(h=h, z=z, r=r, o=o, hr=hr, keep=keep)
+
+    def step_bwd(self, sv, x, dhout, R, G):
+        """x [R,D]: the step's input rows.  Accumulates weight grads into G; returns (dx, dh_prev)."""
+        L, D, st = lib(), self.D, self.st
+        h = sv['h']
+        dpo, dzp, dh = torch.empty_like(h), torch.empty_like(h), torch.empty_like(h)
+        L.gru_bwd_out(ptr(dhout), ptr(sv['keep']), ptr(h), ptr(sv['z']), ptr(sv['o']), ptr(dpo), ptr(dzp),
+                      ptr(dh), R, D, st)
+        dhr = torch.empty_like(h)
+        _gemm(0, 0, R, D, D, dpo, D, self.Wo, 2 * D, dhr, D, st, b_off=D)
+        dzr = _empty((R, 2 * D), h)
+        L.gru_bwd_zr(ptr(dhr), ptr(h), ptr(sv['r']), ptr(sv['z']), ptr(dzp), ptr(dzr), ptr(dh), R, D, st)
+        # dh += dpre_z Wh_z + dpre_r Wh_r
+        _gemm(0, 0, R, D, D, dzr, 2 * D, self.Wz, 2 * D, dh, D, st, beta=1.0, b_off=D)
+        _gemm(0, 0, R, D, D, dzr, 2 * D, self.Wr, 2 * D, dh, D, st, beta=1.0, a_off=D, b_off=D)
+        # dx = dpre_z Wx_z + dpre_r Wx_r + dpre_o Wx_o
+        dx = torch.empty_like(h)
+        _gemm(0, 0, R, D, D, dzr, 2 * D, self.Wz, 2 * D, dx, D, st)
+        _gemm(0, 0, R, D, D, dzr, 2 * D, self.Wr, 2 * D, dx, D, st, beta=1.0, a_off=D)
+        _gemm(0, 0, R, D, D, dpo, D, self.Wo, 2 * D, dx, D, st, beta=1.0)
+        # weight grads: dW[:, :D] += dpre^T x ; dW[:, D:] += dpre^T h (hr for the out gate)
+        for name, A, lda, aoff, hin in (('update_gate', dzr, 2 * D, 0, h), ('reset_gate', dzr, 2 * D, D, h),
+                                         ('out_gate', dpo, D, 0, sv['hr'])):
+            dW = G['agg.cell_list.0.%s.weight' % name]
+            _gemm(1, 0, D, D, R, A, lda, x, D, dW, 2 * D, st, beta=1.0, a_off=aoff)
+            _gemm(1, 0, D, D, R, A, lda, hin, D, dW, 2 * D, st, beta=1.0, a_off=aoff, c_off=D)
+        # biases: column sums of dpre (dzr is [R,2D]: z | r)
+        L.colsum(ptr(dzr), R, 2 * D, ptr(G['_bzr']), 1, st)
+        L.colsum(ptr(dpo), R, D, ptr(G['agg.cell_list.0.out_gate.bias']), 1, st)
+        return dx, dh
+
+
+@_timed('head_fwd')
+def head_forward(z4, dims, B, N, pred_step, P, dropout_p=0.0, seed=0, need_ctx=True):
+    """z4: backbone output rows [B*N*To*S, D] (To temporal slices, S = L*L positions).
+    Returns (score [M, M] with M = B*pred_step*S, ctx)."""
+    L = lib()
+    st = _stream()
+    To, Lh, Lw = dims
+    S, D = Lh * Lw, FEATURE_SIZE
+    NB = B * N
+    Tagg = N - pred_step
+    R = B * S
+    finf_all = _empty((NB * S, D), z4)
+    feat = _empty((NB * S, D), z4)
+    L.pool_split_fwd(ptr(z4), ptr(finf_all), ptr(feat), NB, To, S, D, st)
+    gru = _Gru(P, D, st)
+    # aggregate: x_t rows (b, s) <- feat[(b*N + t)*S + s]
+    X_all = _empty((Tagg * R, D), z4)
+    for t in range(Tagg):
+        L.gather_rows(ptr(feat), X_all.data_ptr() + t * R * D * 4, R, D, S, N * S, t * S, st)
+    XP = gru.xproj(X_all, Tagg * R)
+    h = torch.zeros((R, D), dtype=torch.float32, device=z4.device)
+    steps = []
+    off = 0
+    for t in range(Tagg):
+        h, sv = gru.step(XP, t * R, h, R, dropout_p, seed, off)
+        off += R * D
+        sv['x'] = None          # x_t = X_all[t]
+        steps.append(sv)
+    W0, b0 = P['network_pred.0.weight'], P['network_pred.0.bias']
+    W2, b2 = P['network_pred.2.weight'], P['network_pred.2.bias']
+    M = B * pred_step * S
+    pred_rows = _empty((M, D), z4)
+    psteps = []
+    for i in range(pred_step):
+        u = torch.empty_like(h)
+        _gemm(0, 1, R, D, D, h, D, W0, D, u, D, st)
+        L.bias_relu(ptr(u), ptr(b0), ptr(u), 1, R, D, st)
+        pr = torch.empty_like(h)
+        _gemm(0, 1, R, D, D, u, D, W2, D, pr, D, st)
+        L.bias_relu(ptr(pr), ptr(b2), ptr(pr), 0, R, D, st)
+        L.scatter_rows(ptr(pr), ptr(pred_rows), R, D, S, pred_step * S, i * S, 0, st)
+        rec = dict(h=h, u=u, p=pr)
+        if i < pred_step - 1:                     # the GRU step after the last prediction is dead work
+            xr = torch.empty_like(h)
+            L.bias_relu(ptr(pr), None, ptr(xr), 1, R, D, st)
+            xp = gru.xproj(xr, R)
+            h, sv = gru.step(xp, 0, h, R, dropout_p, seed, off)
+            off += R * D
+            sv['x'] = xr
+            rec['gru'] = sv
+        psteps.append(rec)
+    finf_rows = _empty((M, D), z4)
+    L.gather_rows(ptr(finf_all), ptr(finf_rows), M, D, pred_step * S, N * S, Tagg * S, st)
+    score = _empty((M, M), z4)
+    _gemm(0, 1, M, M, D, pred_rows, D, finf_rows, D, score, M, st)
+    ctx = None
+    if need_ctx:
+        ctx = dict(B=B, N=N, P=pred_step, S=S, D=D, To=To, R=R, M=M, finf_all=finf_all, X_all=X_all,
+                   steps=steps, psteps=psteps, pred_rows=pred_rows, finf_rows=finf_rows)
+    return score, ctx
+
+
+@_timed('head_bwd')
+def head_backward(ctx, dscore, P):
+    """returns (dz4 rows [B*N*To*S, D], grads dict for HEAD_PARAM_NAMES)"""
+    L = lib()
+    st = _stream()
+    B, N, Pn, S, D, To, R, M = (ctx[k] for k in ('B', 'N', 'P', 'S', 'D', 'To', 'R', 'M'))
+    NB, Tagg = B * N, N - Pn
+    dev = dscore.device
+    G = {n: torch.zeros_like(P[n]) for n in HEAD_PARAM_NAMES}
+    G['_bzr'] = torch.zeros(2 * D, dtype=torch.float32, device=dev)     # update | reset bias grads
+    G['agg.cell_list.0.update_gate.bias'] = G['_bzr'][:D]
+    G['agg.cell_list.0.reset_gate.bias'] = G['_bzr'][D:]
+    gru = _Gru(P, D, st)
+    W0, W2 = P['network_pred.0.weight'], P['network_pred.2.weight']
+    dpred_rows = _empty((M, D), dscore)
+    dfinf_rows = _empty((M, D), dscore)
+    _gemm(0, 0, M, D, M, dscore, M, ctx['finf_rows'], D, dpred_rows, D, st)
+    _gemm(1, 0, M, D, M, dscore, M, ctx['pred_rows'], D, dfinf_rows, D, st)
+    dfinf_all = torch.zeros((NB * S, D), dtype=torch.float32, device=dev)
+    L.scatter_rows(ptr(dfinf_rows), ptr(dfinf_all), M, D, Pn * S, N * S, Tagg * S, 0, st)
+    dfeat = torch.zeros((NB * S, D), dtype=torch.float32, device=dev)
+    dh = None
+    for i in reversed(range(Pn)):
+        rec = ctx['psteps'][i]
+        dp = _empty((R, D), dscore)
+        L.gather_rows(ptr(dpred_rows), ptr(dp), R, D, S, Pn * S, i * S, st)
+        if 'gru' in rec:
+            sv = rec['gru']
+            dxr, dh_prev = gru.step_bwd(sv, sv['x'], dh, R, G)
+            L.relu_bwd(ptr(rec['p']), ptr(dxr), ptr(dp), 1, R * D, st)       # dp += dxr * (p > 0)
+            dh = dh_prev
+        # p = u W2^T + b2 ; u = relu(h W0^T + b0)
+        _gemm(1, 0, D, D, R, dp, D, rec['u'], D, G['network_pred.2.weight'], D, st, beta=1.0)
+        L.colsum(ptr(dp), R, D, ptr(G['network_pred.2.bias']), 1, st)
+        du = _empty((R, D), dscore)
+        _gemm(0, 0, R, D, D, dp, D, W2, D, du, D, st)
+        L.relu_bwd(ptr(rec['u']), ptr(du), ptr(du), 0, R * D, st)
+        _gemm(1, 0, D, D, R, du, D, rec['h'], D, G['network_pred.0.weight'], D, st, beta=1.0)
+        L.colsum(ptr(du), R, D, ptr(G['network_pred.0.bias']), 1, st)
+        if dh is None:
+            dh = _empty((R, D), dscore)
+            _gemm(0, 0, R, D, D, du, D, W0, D, dh, D, st)
+        else:
+            _gemm(0, 0, R, D, D, du, D, W0, D, dh, D, st, beta=1.0)
+    X_all = ctx['X_all']
+    for t in reversed(range(Tagg)):
+        x_t = X_all[t * R:(t + 1) * R]
+        dx, dh = gru.step_bwd(ctx['steps'][t], x_t, dh, R, G)
+        L.scatter_rows(ptr(dx), ptr(dfeat), R, D, S, N * S, t * S, 0, st)
+    dz4 = _empty((NB * To * S, D), dscore)
+    L.pool_split_bwd(ptr(ctx['finf_all']), ptr(dfinf_all), ptr(dfeat), ptr(dz4), NB, To, S, D, st)
+    del G['_bzr']
+    return dz4, G
+
+
+# ==================================================================================================
+# NCE mask / loss
+# ==================================================================================================
+def nce_mask(B, P, SQ, device):
+    m = torch.empty((B, P, SQ, B, P, SQ), dtype=torch.int8, device=device)
+    lib().nce_mask_fill(ptr(m), B, P, SQ, _stream())
+    return m
+
+
+def nce_ce_forward(score2d):
+    rows, M = score2d.shape
+    lse = _empty((rows,), score2d)
+    out = _empty((4,), score2d)
+    lib().nce_ce_fwd(ptr(score2d), rows, M, ptr(lse), ptr(out), _stream())
+    return out, lse
+
+
+def nce_ce_backward(score2d, lse, gscale):
+    d = torch.empty_like(score2d)
+    lib().nce_ce_bwd(ptr(score2d), ptr(lse), ptr(gscale), ptr(d), score2d.shape[0], score2d.shape[1], _stream())
+    return d

@@ -1,0 +1,154 @@
+/* dpc_b200.h -- C ABI of libdpc_b200.so: the B200 (sm_100a) kernels behind the DPC-RNN training path.
+ *
+ * The reference (TengdaHan/DPC) has no FFI: its hot path is a chain of stock ATen operators called
+ * from Python nn.Modules.  Each entry point below replaces the operator call sites cited next to
+ * it (paths relative to /root/reference).  The library is loaded with ctypes (dpc_b200/_lib.py);
+ * INTEGRATION.md shows the binding a reference maintainer would add.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer owned by the caller (PyTorch's caching allocator);
+ *     the library never allocates or frees on the hot path and keeps no pointer after returning;
+ *   - `stream` is a cudaStream_t passed as void*; all work is enqueued on it, nothing synchronises;
+ *   - return value: 0 = ok, non-zero = error; dpc_last_error() returns a thread-local message;
+ *   - activations are channels-last rows: a tensor [NB,T,H,W,C] fp32 is `rows = NB*T*H*W` rows of C;
+ *   - no C++ exceptions, no ATen / pybind types cross this boundary.
+ */
+#ifndef DPC_B200_H
+#define DPC_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DPC_B200_ABI_VERSION 1
+
+/* Geometry of one Conv3d call site.  in [NB,Ti,Hi,Wi,Ci] -> out [NB,To,Ho,Wo,Co]. */
+typedef struct dpc_conv_geom {
+    int32_t NB, Ti, Hi, Wi, Ci;
+    int32_t To, Ho, Wo, Co;
+    int32_t kT, kH, kW;
+    int32_t sT, sH, sW;
+    int32_t pT, pH, pW;
+} dpc_conv_geom;
+
+/* ---- library ---------------------------------------------------------------------------- */
+int dpc_abi_version(void);
+const char* dpc_last_error(void);
+/* number of kernel launches issued by this library in this process (bench.py's gpu_launches) */
+int64_t dpc_launch_count(void);
+
+/* ---- Conv3d 1x3x3 / 3x3x3 / 1x1x1, bias-free --------------------------------------------
+ * replaces nn.Conv3d forward/backward at backbone/resnet_2d3d.py:13-31 (conv3x3x3, conv1x3x3),
+ * :241-244 (downsample 1x1x1) as used by BasicBlock2d/3d.forward (:64-80, :100-116).
+ * Weights are consumed in packed form (see dpc_pack_conv_weight). Ci % 16 == 0, Co % 64 == 0. */
+int dpc_pack_conv_weight(const float* w /*[Co,Ci,kT,kH,kW]*/, float* wf /*[taps,Ci,Co]*/,
+                         float* wd /*[taps,Co,Ci]*/, int Co, int Ci, int taps, void* stream);
+int dpc_unpack_conv_wgrad(const float* dwp /*[taps,Ci,Co]*/, float* dw /*[Co,Ci,taps]*/,
+                          int Co, int Ci, int taps, void* stream);
+int dpc_conv3d_fwd(const dpc_conv_geom* g, const float* x, const float* wf, float* y, void* stream);
+/* dx = dgrad (accumulate == 0) or dx += dgrad (accumulate != 0) */
+int dpc_conv3d_dgrad(const dpc_conv_geom* g, const float* dy, const float* wd, float* dx,
+                     int accumulate, void* stream);
+/* dwp [taps,Ci,Co] is overwritten */
+int dpc_conv3d_wgrad(const dpc_conv_geom* g, const float* x, const float* dy, float* dwp, void* stream);
+
+/* ---- stem: Conv3d(3,64,(1,7,7),s(1,2,2),p(0,3,3)) reading the caller's NCDHW input ----------
+ * replaces backbone/resnet_2d3d.py:211,260 (self.conv1).  x [NB,3,T,H,W] -> y [NB,T,H/2,W/2,64]. */
+int dpc_stem_conv_fwd(const float* x, const float* w /*[64,3,1,7,7]*/, float* y,
+                      int NB, int T, int H, int W, void* stream);
+int dpc_stem_conv_wgrad(const float* x, const float* dy, float* dw /*[64,3,1,7,7]*/,
+                        int NB, int T, int H, int W, void* stream);
+
+/* ---- BatchNorm3d(track_running_stats=False): batch statistics always ----------------------
+ * replaces nn.BatchNorm3d at resnet_2d3d.py:55,59,91,95,212,243 (+ relu_ / `out += residual`
+ * at :68-78,:104-114).  Biased variance, eps as given (1e-5).  `ws` = 2*C doubles of scratch. */
+int dpc_bn_stats(const float* y, int64_t rows, int C, double* ws, float* mean, float* rstd,
+                 float eps, void* stream);
+/* out = [relu]( bn(y) + residual ), residual = none | res | bn_r(res)  (downsample branch) */
+int dpc_bn_apply_fwd(const float* y, const float* mean, const float* rstd, const float* gamma,
+                     const float* beta, const float* res, const float* r_mean, const float* r_rstd,
+                     const float* r_gamma, const float* r_beta, int relu, float* out,
+                     int64_t rows, int C, void* stream);
+/* backward of the above for ONE BatchNorm: g = dout * (out > 0 if relu), then
+ * dgamma = sum g*xhat, dbeta = sum g, dy = gamma*rstd*(g - dbeta/n - xhat*dgamma/n).
+ * g_out (nullable) receives g (the gradient of the identity residual). `ws` = 2*C doubles. */
+int dpc_bn_bwd(const float* dout, const float* out, int relu, const float* y, const float* mean,
+               const float* rstd, const float* gamma, double* ws, float* dgamma, float* dbeta,
+               float* dy, float* g_out, int64_t rows, int C, void* stream);
+
+/* ---- stem tail: BN + ReLU + MaxPool3d((1,3,3),s(1,2,2),p(0,1,1)) in one pass ---------------
+ * replaces resnet_2d3d.py:212-214,261-263.  y [NB*T,H,W,C] -> out [NB*T,H/2,W/2,C]. */
+int dpc_bn_relu_maxpool_fwd(const float* y, const float* mean, const float* rstd, const float* gamma,
+                            const float* beta, float* out, int NT, int H, int W, int C, void* stream);
+/* g [NB*T,H,W,C] = gradient w.r.t. bn(y) (ReLU and pool already undone), from dout on the pooled grid */
+int dpc_bn_relu_maxpool_bwd(const float* y, const float* mean, const float* rstd, const float* gamma,
+                            const float* beta, const float* out, const float* dout, float* g,
+                            int NT, int H, int W, int C, void* stream);
+
+/* ---- temporal average + ReLU split --------------------------------------------------------
+ * replaces F.avg_pool3d / self.relu at dpc/model_3d.py:53-57.  z [NB,T,S,C] ->
+ * finf [NB,S,C] (mean over T, pre-ReLU) and feat [NB,S,C] (ReLU). */
+int dpc_pool_split_fwd(const float* z, float* finf, float* feat, int NB, int T, int S, int C, void* stream);
+int dpc_pool_split_bwd(const float* finf, const float* dfinf, const float* dfeat, float* dz,
+                       int NB, int T, int S, int C, void* stream);
+
+/* ---- dense helpers used by the ConvGRU / predictor / score stages ---------------------------
+ * C[M,N] (ldc) = alpha * opA(A) * opB(B) + beta * C;  row-major; transX != 0 means the operand is
+ * stored transposed.  fp32 CUDA-core GEMM: the small (latency-bound) GEMMs of convrnn.py:29-33 and
+ * model_3d.py:36-40,68. */
+int dpc_gemm_f32(int transA, int transB, int M, int N, int K, float alpha, const float* A, int lda,
+                 const float* B, int ldb, float beta, float* C, int ldc, void* stream);
+/* dst[r] = src[(r / inner) * outer + offset + r % inner]  (rows of D floats) */
+int dpc_gather_rows(const float* src, float* dst, int64_t rows, int D, int64_t inner, int64_t outer,
+                    int64_t offset, void* stream);
+/* dst[(r / inner) * outer + offset + r % inner] (+)= src[r] */
+int dpc_scatter_rows(const float* src, float* dst, int64_t rows, int D, int64_t inner, int64_t outer,
+                     int64_t offset, int accumulate, void* stream);
+/* colsum[n] (+)= sum_r A[r,n] */
+int dpc_colsum(const float* A, int64_t rows, int N, float* out, int accumulate, void* stream);
+
+/* ---- ConvGRU cell (kernel_size 1) gate math ------------------------------------------------
+ * replaces torch.sigmoid / tanh / mul / add / Dropout at backbone/convrnn.py:29-33,78.
+ * pre-activations come from dpc_gemm_f32; all tensors [R,D] unless noted. */
+int dpc_gru_gates_zr(const float* xz, const float* xr, int ldx, const float* hzr /*[R,2D]: z|r*/,
+                     const float* bz, const float* br, const float* h, float* z, float* r,
+                     float* hr, int64_t R, int D, void* stream);
+/* o = tanh(xo + ho + bo); hn = h*(1-z) + o*z; hout = hn * keep(seed,step)/(1-p) (p == 0: no dropout) */
+int dpc_gru_out(const float* xo, int ldx, const float* ho, const float* bo, const float* h,
+                const float* z, float* o, float* hout, float* keep /*nullable [R,D]*/,
+                float p, uint64_t seed, uint64_t offset, int64_t R, int D, void* stream);
+/* backward of one cell step, elementwise part (see dpc_b200/engine.py for the GEMMs around it) */
+int dpc_gru_bwd_out(const float* dhout, const float* keep, const float* h, const float* z,
+                    const float* o, float* dpre_o, float* dpre_z_partial, float* dh, int64_t R, int D,
+                    void* stream);
+int dpc_gru_bwd_zr(const float* dhr, const float* h, const float* r, const float* z,
+                   const float* dz_partial, float* dpre_zr /*[R,2D]*/, float* dh /*accumulated*/,
+                   int64_t R, int D, void* stream);
+/* y = relu(x + b) (b nullable) and its backward */
+int dpc_bias_relu(const float* x, const float* b, float* y, int relu, int64_t R, int D, void* stream);
+int dpc_relu_bwd(const float* y, const float* dy, float* dx, int accumulate, int64_t n, void* stream);
+
+/* ---- NCE score / mask / cross-entropy -------------------------------------------------------
+ * mask: closed form of the Python loops at dpc/model_3d.py:86-96 (values {1,-1,-3,0}, contiguous).
+ * ce: nn.CrossEntropyLoss(mean) with target = diagonal, dpc/main.py:178-185,213-217, and
+ * calc_topk_accuracy (utils/utils.py:38-55) for k = 1,3,5. */
+int dpc_nce_mask_fill(int8_t* mask, int B, int P, int SQ, void* stream);
+/* score [rows, M]; positive of row i = column i % M (rows == M on one device; rows = n_gpu*M
+ * after the reference's DataParallel gather).  out[0] = loss, out[1..3] = top1/3/5 accuracy;
+ * lse[rows] saved for backward */
+int dpc_nce_ce_fwd(const float* score, int rows, int M, float* lse, float* out, void* stream);
+/* dscore = gscale[0] * (softmax - onehot) / rows   (gscale: device scalar, nullable = 1) */
+int dpc_nce_ce_bwd(const float* score, const float* lse, const float* gscale, float* dscore,
+                   int rows, int M, void* stream);
+
+/* ---- optimiser ------------------------------------------------------------------------------
+ * torch.optim.Adam(lr, weight_decay) (L2, not AdamW), dpc/main.py:81,231, over a flat buffer. */
+int dpc_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1,
+                  float beta2, float eps, float wd, int step, float gscale, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DPC_B200_H */

@@ -1,0 +1,298 @@
+"""GPU: every C-ABI kernel family against a plain PyTorch fp32 reference of the same op
+(CUDA, TF32 disabled), called through ctypes exactly like the product path does."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope='module', autouse=True)
+def _fp32_reference_math():
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    yield
+
+
+def _lib():
+    from dpc_b200._lib import lib
+    return lib()
+
+
+def _st():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def rel(a, b):
+    a, b = a.double(), b.double()
+    return float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
+
+
+def to_rows(x):      # NCDHW -> [rows, C]
+    return x.permute(0, 2, 3, 4, 1).contiguous().view(-1, x.shape[1])
+
+
+def from_rows(r, NB, T, H, W):
+    return r.view(NB, T, H, W, -1).permute(0, 4, 1, 2, 3).contiguous()
+
+
+CONV_CASES = [
+    # NB, T, H, W, Ci, Co, k, s, p
+    (3, 5, 16, 16, 64, 64, (1, 3, 3), (1, 1, 1), (0, 1, 1)),
+    (2, 5, 16, 16, 64, 128, (1, 3, 3), (1, 2, 2), (0, 1, 1)),
+    (2, 5, 16, 16, 64, 128, (1, 1, 1), (1, 2, 2), (0, 0, 0)),
+    (3, 5, 8, 8, 128, 256, (3, 3, 3), (2, 2, 2), (1, 1, 1)),
+    (3, 5, 8, 8, 128, 256, (1, 1, 1), (2, 2, 2), (0, 0, 0)),
+    (3, 3, 4, 4, 256, 256, (3, 3, 3), (1, 1, 1), (1, 1, 1)),
+    (5, 3, 7, 7, 256, 256, (3, 3, 3), (2, 2, 2), (1, 1, 1)),       # odd extents (224^2 path)
+    (1, 2, 2, 2, 256, 256, (3, 3, 3), (1, 1, 1), (1, 1, 1)),       # smaller than one tile
+]
+
+
+@pytest.mark.parametrize('case', CONV_CASES)
+def test_conv3d_fwd_dgrad_wgrad(case):
+    from dpc_b200.engine import ConvSite
+    NB, T, H, W, Ci, Co, k, s, p = case
+    g = torch.Generator(device='cuda').manual_seed(1)
+    x = torch.randn(NB, Ci, T, H, W, device='cuda', generator=g)
+    w = torch.randn(Co, Ci, *k, device='cuda', generator=g) / math.sqrt(Ci * k[0] * k[1] * k[2])
+    site = ConvSite(NB, (T, H, W), Ci, Co, k, s, p)
+    site.pack(w, _st())
+    xr = to_rows(x)
+    y = site.fwd(xr, _st())
+    xref = x.clone().requires_grad_(True)
+    wref = w.clone().requires_grad_(True)
+    yref = F.conv3d(xref, wref, None, s, p)
+    To, Ho, Wo = site.dims_out
+    assert tuple(yref.shape[2:]) == (To, Ho, Wo)
+    assert rel(from_rows(y, NB, To, Ho, Wo), yref) < 2e-5
+    dy = torch.randn(yref.shape, device='cuda', generator=g)
+    yref.backward(dy)
+    dyr = to_rows(dy)
+    dx = site.dgrad(dyr, _st())
+    assert rel(from_rows(dx, NB, T, H, W), xref.grad) < 2e-5
+    base = torch.randn_like(xr)
+    dx2 = site.dgrad(dyr, _st(), dx=base.clone())
+    assert rel(dx2 - base, to_rows(xref.grad)) < 5e-5
+    dw = site.wgrad(xr, dyr, _st())
+    assert dw.shape == w.shape
+    assert rel(dw, wref.grad) < 5e-5
+
+
+@pytest.mark.parametrize('NB,T,H,W', [(2, 5, 64, 64), (3, 2, 32, 48), (1, 1, 28, 20)])
+def test_stem_conv(NB, T, H, W):
+    L = _lib()
+    g = torch.Generator(device='cuda').manual_seed(2)
+    x = torch.randn(NB, 3, T, H, W, device='cuda', generator=g)
+    w = torch.randn(64, 3, 1, 7, 7, device='cuda', generator=g) * 0.1
+    Ho, Wo = (H - 1) // 2 + 1, (W - 1) // 2 + 1
+    y = torch.empty(NB * T * Ho * Wo, 64, device='cuda')
+    L.stem_conv_fwd(x.data_ptr(), w.data_ptr(), y.data_ptr(), NB, T, H, W, _st())
+    xr, wr = x.clone(), w.clone().requires_grad_(True)
+    yref = F.conv3d(xr, wr, None, (1, 2, 2), (0, 3, 3))
+    assert tuple(yref.shape[2:]) == (T, Ho, Wo)
+    assert rel(from_rows(y, NB, T, Ho, Wo), yref) < 2e-5
+    dy = torch.randn(yref.shape, device='cuda', generator=g)
+    yref.backward(dy)
+    dw = torch.empty_like(w)
+    L.stem_conv_wgrad(x.data_ptr(), to_rows(dy).data_ptr(), dw.data_ptr(), NB, T, H, W, _st())
+    assert rel(dw, wr.grad) < 5e-5
+
+
+@pytest.mark.parametrize('C,rows', [(64, 5000), (128, 1237), (256, 96)])
+@pytest.mark.parametrize('mode', ['plain', 'res', 'resbn'])
+@pytest.mark.parametrize('relu', [True, False])
+def test_bn_fwd_bwd(C, rows, mode, relu):
+    from dpc_b200 import engine as E
+    g = torch.Generator(device='cuda').manual_seed(3)
+    y = torch.randn(rows, C, device='cuda', generator=g) * 2 + 0.5
+    gamma = torch.rand(C, device='cuda', generator=g) + 0.5
+    beta = torch.randn(C, device='cuda', generator=g) * 0.1
+    res = torch.randn(rows, C, device='cuda', generator=g)
+    gr = torch.rand(C, device='cuda', generator=g) + 0.5
+    br = torch.randn(C, device='cuda', generator=g) * 0.1
+    st = _st()
+    mean, rstd = E._bn_stats(y, rows, C, st)
+    assert rel(mean, y.mean(0)) < 1e-5
+    assert rel(rstd, 1 / torch.sqrt(y.var(0, unbiased=False) + 1e-5)) < 1e-5
+    yr = y.clone().requires_grad_(True)
+    gam, bet = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
+    rr = res.clone().requires_grad_(True)
+    grr, brr = gr.clone().requires_grad_(True), br.clone().requires_grad_(True)
+    ref = F.batch_norm(yr, None, None, gam, bet, True, 0.0, 1e-5)
+    if mode == 'plain':
+        out = E._bn_apply(y, mean, rstd, gamma, beta, relu, rows, C, st)
+    elif mode == 'res':
+        out = E._bn_apply(y, mean, rstd, gamma, beta, relu, rows, C, st, res=res)
+        ref = ref + rr
+    else:
+        mr, sr = E._bn_stats(res, rows, C, st)
+        out = E._bn_apply(y, mean, rstd, gamma, beta, relu, rows, C, st, res=res, rbn=(mr, sr, gr, br))
+        ref = ref + F.batch_norm(rr, None, None, grr, brr, True, 0.0, 1e-5)
+    if relu:
+        ref = F.relu(ref)
+    assert rel(out, ref) < 1e-5
+    dout = torch.randn(rows, C, device='cuda', generator=g)
+    ref.backward(dout)
+    dy, dg, db, gbuf = E._bn_bwd(dout, out, relu, y, mean, rstd, gamma, rows, C, st, want_g=True)
+    assert rel(dy, yr.grad) < 5e-5
+    assert rel(dg, gam.grad) < 5e-5
+    assert rel(db, bet.grad) < 5e-5
+    if mode == 'res':
+        assert rel(gbuf, rr.grad) < 1e-6
+    if mode == 'resbn':
+        dyr, dgr, dbr, _ = E._bn_bwd(dout, out, relu, res, mr, sr, gr, rows, C, st)
+        assert rel(dyr, rr.grad) < 5e-5
+        assert rel(dgr, grr.grad) < 5e-5
+
+
+@pytest.mark.parametrize('NT,H,W', [(6, 32, 32), (3, 16, 24), (2, 7, 9)])
+def test_bn_relu_maxpool(NT, H, W):
+    from dpc_b200 import engine as E
+    L = _lib()
+    C = 64
+    g = torch.Generator(device='cuda').manual_seed(4)
+    y = torch.randn(NT * H * W, C, device='cuda', generator=g)
+    gamma = torch.rand(C, device='cuda', generator=g) + 0.5
+    beta = torch.randn(C, device='cuda', generator=g) * 0.1
+    st = _st()
+    mean, rstd = E._bn_stats(y, NT * H * W, C, st)
+    Ho, Wo = (H - 1) // 2 + 1, (W - 1) // 2 + 1
+    out = torch.empty(NT * Ho * Wo, C, device='cuda')
+    L.bn_relu_maxpool_fwd(y.data_ptr(), mean.data_ptr(), rstd.data_ptr(), gamma.data_ptr(), beta.data_ptr(),
+                          out.data_ptr(), NT, H, W, C, st)
+    # reference: treat NT as the batch, one "frame" each
+    yr = y.view(NT, H, W, C).permute(0, 3, 1, 2).unsqueeze(2).contiguous().requires_grad_(True)   # [NT,C,1,H,W]
+    gam, bet = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
+    a = F.relu(F.batch_norm(yr, None, None, gam, bet, True, 0.0, 1e-5))
+    a.retain_grad()
+    ref = F.max_pool3d(a, (1, 3, 3), (1, 2, 2), (0, 1, 1))
+    assert tuple(ref.shape[3:]) == (Ho, Wo)
+    ref_rows = ref.squeeze(2).permute(0, 2, 3, 1).reshape(-1, C)
+    assert rel(out, ref_rows) < 1e-5
+    dout = torch.randn(NT * Ho * Wo, C, device='cuda', generator=g)
+    ref.backward(dout.view(NT, Ho, Wo, C).permute(0, 3, 1, 2).unsqueeze(2))
+    gbuf = torch.empty_like(y)
+    L.bn_relu_maxpool_bwd(y.data_ptr(), mean.data_ptr(), rstd.data_ptr(), gamma.data_ptr(), beta.data_ptr(),
+                          out.data_ptr(), dout.data_ptr(), gbuf.data_ptr(), NT, H, W, C, st)
+    # gbuf = grad wrt bn(y) output (ReLU mask applied); compare through the BN backward
+    dy, dg, db, _ = E._bn_bwd(gbuf, None, False, y, mean, rstd, gamma, NT * H * W, C, st)
+    dy_ref = yr.grad.squeeze(2).permute(0, 2, 3, 1).reshape(-1, C)
+    assert rel(dy, dy_ref) < 5e-5
+    assert rel(dg, gam.grad) < 5e-5
+
+
+def test_pool_split():
+    L = _lib()
+    NB, T, S, C = 6, 2, 16, 256
+    g = torch.Generator(device='cuda').manual_seed(5)
+    z = torch.randn(NB, T, S, C, device='cuda', generator=g)
+    finf, feat = torch.empty(NB, S, C, device='cuda'), torch.empty(NB, S, C, device='cuda')
+    L.pool_split_fwd(z.data_ptr(), finf.data_ptr(), feat.data_ptr(), NB, T, S, C, _st())
+    zr = z.clone().requires_grad_(True)
+    m = zr.mean(1)
+    assert rel(finf, m) < 1e-6 and rel(feat, F.relu(m)) < 1e-6
+    d1, d2 = torch.randn_like(finf), torch.randn_like(finf)
+    (m * d1 + F.relu(m) * d2).sum().backward()
+    dz = torch.empty_like(z)
+    L.pool_split_bwd(finf.data_ptr(), d1.data_ptr(), d2.data_ptr(), dz.data_ptr(), NB, T, S, C, _st())
+    assert rel(dz, zr.grad) < 1e-6
+
+
+@pytest.mark.parametrize('ta,tb', [(0, 0), (0, 1), (1, 0), (1, 1)])
+@pytest.mark.parametrize('M,N,K', [(200, 256, 512), (96, 96, 256), (33, 70, 19)])
+def test_gemm_f32(ta, tb, M, N, K):
+    L = _lib()
+    g = torch.Generator(device='cuda').manual_seed(6)
+    A = torch.randn((K, M) if ta else (M, K), device='cuda', generator=g)
+    B = torch.randn((N, K) if tb else (K, N), device='cuda', generator=g)
+    C0 = torch.randn(M, N, device='cuda', generator=g)
+    C = C0.clone()
+    L.gemm_f32(ta, tb, M, N, K, 0.5, A.data_ptr(), A.shape[1], B.data_ptr(), B.shape[1], 2.0, C.data_ptr(), N, _st())
+    ref = 0.5 * ((A.t() if ta else A).double() @ (B.t() if tb else B).double()) + 2.0 * C0.double()
+    assert rel(C, ref) < 1e-5
+
+
+def test_rows_and_colsum():
+    L = _lib()
+    g = torch.Generator(device='cuda').manual_seed(7)
+    B, N, S, D, P = 3, 8, 4, 256, 3
+    feat = torch.randn(B * N * S, D, device='cuda', generator=g)
+    for t in (0, 4):
+        dst = torch.empty(B * S, D, device='cuda')
+        L.gather_rows(feat.data_ptr(), dst.data_ptr(), B * S, D, S, N * S, t * S, _st())
+        assert torch.equal(dst, feat.view(B, N, S, D)[:, t].reshape(B * S, D))
+    dst = torch.empty(B * P * S, D, device='cuda')
+    L.gather_rows(feat.data_ptr(), dst.data_ptr(), B * P * S, D, P * S, N * S, (N - P) * S, _st())
+    assert torch.equal(dst, feat.view(B, N, S, D)[:, N - P:].reshape(-1, D))
+    back = torch.zeros_like(feat)
+    L.scatter_rows(dst.data_ptr(), back.data_ptr(), B * P * S, D, P * S, N * S, (N - P) * S, 0, _st())
+    assert torch.equal(back.view(B, N, S, D)[:, N - P:].reshape(-1, D), dst)
+    assert float(back.view(B, N, S, D)[:, :N - P].abs().max()) == 0.0
+    A = torch.randn(1000, 512, device='cuda', generator=g)
+    out = torch.ones(512, device='cuda')
+    L.colsum(A.data_ptr(), 1000, 512, out.data_ptr(), 1, _st())
+    assert rel(out, A.double().sum(0) + 1) < 1e-5
+
+
+@pytest.mark.parametrize('B,P,SQ', [(2, 3, 4), (3, 2, 9), (5, 3, 16)])
+def test_nce_mask_and_ce(B, P, SQ):
+    from dpc_b200 import engine as E
+    from oracle import dpc_oracle as O
+    m = E.nce_mask(B, P, SQ, torch.device('cuda'))
+    ref = O.closed_form_mask(B, P, int(math.isqrt(SQ)))
+    assert m.dtype == torch.int8 and m.is_contiguous()
+    assert torch.equal(m.cpu(), ref)
+    M = B * P * SQ
+    g = torch.Generator(device='cuda').manual_seed(8)
+    for rows in (M, 2 * M):                        # square (1 GPU) and DataParallel-gathered (2 replicas)
+        score = (torch.randn(rows, M, device='cuda', generator=g) * 3).requires_grad_(True)
+        target = torch.arange(rows, device='cuda') % M
+        ref_loss = F.cross_entropy(score, target)
+        ref_loss.backward()
+        out, lse = E.nce_ce_forward(score.detach())
+        assert abs(float(out[0]) - float(ref_loss)) < 1e-5 * max(1.0, abs(float(ref_loss)))
+        tk = O.topk_accuracy(score.detach(), target)
+        for i in range(3):
+            assert abs(float(out[1 + i]) - float(tk[i])) < 1e-6
+        gs = torch.tensor([0.7], device='cuda')
+        d = E.nce_ce_backward(score.detach(), lse, gs)
+        assert rel(d, 0.7 * score.grad) < 1e-5
+
+
+def test_adam_step():
+    from oracle import dpc_oracle as O
+    L = _lib()
+    n = 100003
+    g = torch.Generator(device='cuda').manual_seed(9)
+    p = torch.randn(n, device='cuda', generator=g)
+    m, v = torch.zeros_like(p), torch.zeros_like(p)
+    pref = {'p': p.clone().cpu()}
+    st = {}
+    for step in range(1, 4):
+        grad = torch.randn(n, device='cuda', generator=g)
+        L.adam_step(p.data_ptr(), grad.data_ptr(), m.data_ptr(), v.data_ptr(), n, 1e-3, 0.9, 0.999, 1e-8, 1e-5,
+                    step, 0.5, _st())
+        O.adam_step(pref, {'p': (grad * 0.5).cpu()}, st)
+    assert rel(p.cpu(), pref['p']) < 1e-6
+
+
+def test_gru_cell_matches_oracle():
+    """one fused ConvGRU step (GEMMs + gate kernels) vs oracle.gru_cell, eval mode"""
+    from dpc_b200 import engine as E
+    from oracle import dpc_oracle as O
+    B, L_, D = 3, 2, 256
+    sd = O.synthetic_state_dict('resnet18', 5)
+    P = {k: v.cuda() for k, v in sd.items()}
+    g = torch.Generator().manual_seed(10)
+    x = torch.randn(B, D, L_, L_, generator=g)
+    h = torch.randn(B, D, L_, L_, generator=g)
+    ref = O.gru_cell(x, h, sd)
+    rows = lambda t: t.permute(0, 2, 3, 1).reshape(-1, D).contiguous().cuda()
+    gru = E._Gru(P, D, _st())
+    xr, hr = rows(x), rows(h)
+    XP = gru.xproj(xr, B * L_ * L_)
+    hn, _ = gru.step(XP, 0, hr, B * L_ * L_, 0.0, 0, 0)
+    assert rel(hn.cpu(), rows(ref).cpu()) < 2e-5

@@ -1,0 +1,183 @@
+"""GPU parity of the product path (dpc_b200.DPC_RNN, through the C ABI) against the CPU oracle and the
+golden vectors the live reference produced (tests/golden/, oracle/make_golden.py).
+
+Tolerance: the north star's 1e-3 relative fp32 (max|a-b| / max|b|) for feature maps, score and loss;
+mask bit-exact; parameter gradients at a looser, stated 5e-3 (backward sums cancel heavily in BN)."""
+import io
+import contextlib
+
+import pytest
+import torch
+
+from tests.util import CASES, load_fixture, make_block, rel_err, check_sample
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-3
+GRAD_TOL = 5e-3
+
+
+def build(network, img, pred_step, sd):
+    import dpc_b200
+    with contextlib.redirect_stdout(io.StringIO()):
+        m = dpc_b200.DPC_RNN(sample_size=img, num_seq=8, seq_len=5, network=network, pred_step=pred_step)
+    m.load_state_dict(sd, strict=True)
+    return m.cuda()
+
+
+@pytest.mark.parametrize('case', CASES)
+def test_forward_vs_golden_and_oracle(case):
+    from oracle import dpc_oracle as O
+    fx = load_fixture(case)
+    sd = O.synthetic_state_dict(fx['network'], fx['seed_w'])
+    m = build(fx['network'], fx['img'], fx['pred_step'], sd).eval()
+    block = make_block(fx)
+    with torch.no_grad():
+        score, mask = m(block.cuda())
+    assert mask.dtype == torch.int8 and mask.is_contiguous()
+    assert torch.equal(mask.cpu(), fx['mask'])                      # bit-exact vs the reference's loops
+    e, l2 = rel_err(score, fx['score'])
+    assert e < TOL and l2 < TOL, (e, l2)
+    # backbone feature map vs the reference's hook
+    with torch.no_grad():
+        feat = m.backbone(block.view(-1, 3, 5, fx['img'], fx['img']).cuda())
+    assert feat.shape == fx['backbone_out'].shape
+    e, l2 = rel_err(feat, fx['backbone_out'])
+    assert e < TOL and l2 < TOL, (e, l2)
+    # fused criterion vs the driver-side CE + top-k
+    import dpc_b200
+    crit = dpc_b200.NCECriterion()
+    loss = crit(score, fx['target'].cuda())
+    assert abs(float(loss) - fx['loss']) < TOL * max(1.0, abs(fx['loss']))
+    assert [round(float(t), 5) for t in crit.topk] == [round(t, 5) for t in fx['topk']]
+
+
+@pytest.mark.parametrize('case', ['r18_img64_b2', 'r34_img64_b3'])
+def test_grads_vs_golden(case):
+    """loss.backward() through the unchanged driver-side loss (torch CE on our score)."""
+    from oracle import dpc_oracle as O
+    fx = load_fixture(case)
+    sd = O.synthetic_state_dict(fx['network'], fx['seed_w'])
+    m = build(fx['network'], fx['img'], fx['pred_step'], sd).eval()
+    block = make_block(fx).cuda()
+    score, mask = m(block)
+    B, P, SQ = mask.shape[:3]
+    target = (mask == 1).view(B * P * SQ, -1).to(int).argmax(1)     # main.py:214-215 on OUR contiguous mask
+    loss = torch.nn.functional.cross_entropy(score.view(B * P * SQ, -1), target)
+    assert abs(float(loss) - fx['loss']) < TOL * max(1.0, abs(fx['loss']))
+    loss.backward()
+    worst = 0.0
+    for k, p in m.named_parameters():
+        s = fx['grads'][k]
+        assert p.grad is not None, k
+        worst = max(worst, check_sample(p.grad, s, GRAD_TOL, k))
+    print('worst sampled grad rel err', worst)
+
+
+def test_fused_criterion_grads_equal_torch_ce():
+    from oracle import dpc_oracle as O
+    import dpc_b200
+    fx = load_fixture('r18_img64_b2')
+    sd = O.synthetic_state_dict(fx['network'], fx['seed_w'])
+    block = make_block(fx).cuda()
+    grads = []
+    for fused in (False, True):
+        m = build(fx['network'], fx['img'], fx['pred_step'], sd).eval()
+        score, mask = m(block)
+        M = score.shape[0] * score.shape[1] * score.shape[2]
+        if fused:
+            loss = dpc_b200.NCECriterion()(score)
+        else:
+            loss = torch.nn.functional.cross_entropy(score.view(M, M), torch.arange(M, device='cuda'))
+        loss.backward()
+        grads.append({k: p.grad.clone() for k, p in m.named_parameters()})
+    for k in grads[0]:
+        e, _ = rel_err(grads[1][k], grads[0][k])
+        assert e < 1e-4, (k, e)
+
+
+def test_train_mode_dropout_matches_oracle_with_same_masks():
+    """train(): GRU dropout is live (SURVEY.md §3.4 trap 1).  Feed OUR keep masks to the oracle."""
+    from oracle import dpc_oracle as O
+    from dpc_b200 import engine as E
+    network, img, B, N, P = 'resnet18', 64, 2, 8, 3
+    sd = O.synthetic_state_dict(network, 31)
+    Pd = {k: v.cuda() for k, v in sd.items()}
+    g = torch.Generator().manual_seed(32)
+    block = torch.randn(B, N, 3, 5, img, img, generator=g)
+    bb = {k[len('backbone.'):]: v for k, v in Pd.items() if k.startswith('backbone.')}
+    rows, dims, _ = E.backbone_forward(network, block.view(B * N, 3, 5, img, img).cuda().contiguous(), bb, need_ctx=False)
+    score, ctx = E.head_forward(rows, dims, B, N, P, Pd, dropout_p=0.1, seed=1234)
+    L = dims[1]
+    keeps = [sv['keep'] for sv in ctx['steps']] + [r['gru']['keep'] for r in ctx['psteps'] if 'gru' in r]
+    assert len(keeps) == (N - P) + (P - 1)
+    frac = float(torch.stack(keeps).eq(0).float().mean())
+    assert 0.07 < frac < 0.13                                        # p = 0.1
+    vals = torch.stack(keeps).unique()
+    assert all(abs(float(v)) < 1e-9 or abs(float(v) - 1 / 0.9) < 1e-6 for v in vals)
+    masks = [k.view(B, L, L, 256).permute(0, 3, 1, 2).cpu() for k in keeps]
+    ref_score, _ = O.dpc_forward(block, sd, network, P, dropout_masks=masks)
+    e, l2 = rel_err(score.view(-1), ref_score.reshape(-1))
+    assert e < TOL and l2 < TOL, (e, l2)
+    # and two train-mode forwards differ (different seeds)
+    score2, _ = E.head_forward(rows, dims, B, N, P, Pd, dropout_p=0.1, seed=99, need_ctx=False)
+    assert float((score2 - score).abs().max()) > 1e-3
+
+
+def test_train_step_vs_oracle_adam():
+    """one full step: forward, fused NCE, backward, flat-buffer Adam -- parameters after the step
+    against the oracle's (autograd + restated torch.optim.Adam), eval-mode forward for determinism."""
+    from oracle import dpc_oracle as O
+    import dpc_b200
+    fx = load_fixture('r18_img64_b2')
+    sd = O.synthetic_state_dict(fx['network'], fx['seed_w'])
+    m = build(fx['network'], fx['img'], fx['pred_step'], sd).eval()
+    tr = dpc_b200.FlatTrainer(m, lr=1e-3, weight_decay=1e-5)
+    block = make_block(fx)
+    tr.zero_grad()
+    score, _ = m(block.cuda())
+    loss = dpc_b200.NCECriterion()(score)
+    loss.backward()
+    tr.step()
+    uniq = {k: v.clone() for k, v in sd.items() if not k.startswith('agg.ConvGRUCell_00')}
+    _, _, grads = O.train_step_grads(block, sd, fx['network'], fx['pred_step'])
+    O.adam_step(uniq, grads, {})
+    new = m.state_dict()
+    for k, v in uniq.items():
+        # the first Adam step moves every weight by ~lr * sign(g): compare the update direction
+        d_ours = (new[k].cpu() - sd[k]).reshape(-1)
+        d_ref = (v - sd[k]).reshape(-1)
+        cos = float(torch.dot(d_ours.double(), d_ref.double()) / (d_ours.double().norm() * d_ref.double().norm() + 1e-30))
+        assert cos > 0.99, (k, cos)
+
+
+def test_moderate_size_against_oracle_on_device():
+    """B=8 at 128^2 (1/16 of BASELINE config 2): compare with the oracle run on the GPU in fp32
+    (TF32 off) -- the same functional restatement, different device."""
+    from oracle import dpc_oracle as O
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    network, img, B = 'resnet18', 128, 8
+    sd = O.synthetic_state_dict(network, 41)
+    m = build(network, img, 3, sd).eval()
+    g = torch.Generator().manual_seed(42)
+    block = torch.randn(B, 8, 3, 5, img, img, generator=g).cuda()
+    score, mask = m(block)
+    loss = __import__('dpc_b200').NCECriterion()(score)
+    loss.backward()
+    sdc = {k: v.cuda() for k, v in sd.items()}
+    ref_loss, ref_score, ref_grads = O.train_step_grads(block, sdc, network, 3)
+    e, l2 = rel_err(score, ref_score)
+    assert e < TOL and l2 < TOL, (e, l2)
+    assert abs(float(loss) - float(ref_loss)) < TOL * max(1.0, abs(float(ref_loss)))
+    for k, p in m.named_parameters():
+        e, l2 = rel_err(p.grad, ref_grads[k])
+        assert l2 < GRAD_TOL, (k, e, l2)
+
+
+def test_no_cpu_fallback():
+    import dpc_b200
+    with contextlib.redirect_stdout(io.StringIO()):
+        m = dpc_b200.DPC_RNN(64, network='resnet18')
+    with pytest.raises(RuntimeError):
+        m(torch.randn(1, 8, 3, 5, 64, 64))                          # CPU tensor: loud failure, no fallback
