@@ -51,6 +51,12 @@ def workload(a, n):
                   % (a.batch_size * 8 * 3 * 5 * a.img_dim ** 2 * 4 / 1e9)}
 
 
+def cpu_threads():
+    """host threads for the CPU arm: all cores up to 32 -- torch's CPU conv3d backward gets SLOWER beyond
+    that on the 128-core GPU hosts (measured 14-94 s/step at 128 threads vs ~1.5 s at 8-32)"""
+    return max(1, min(os.cpu_count() or 1, int(os.environ.get('DPC_CPU_THREADS', 32))))
+
+
 def measured_peaks():
     p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
     if os.path.exists(p):
@@ -117,9 +123,9 @@ def run_reference(a, rank, world):
         return
     import torch
     from oracle import dpc_oracle as O
-    torch.set_num_threads(os.cpu_count() or 1)
+    torch.set_num_threads(cpu_threads())
     bs = 4
-    t = O.cpu_train_step_time(a.net, a.img_dim, batch=bs, steps=max(1, a.steps), warmup=max(1, min(a.warmup, 2)))
+    t = O.cpu_train_step_time(a.net, a.img_dim, batch=bs, steps=max(1, min(a.steps, 5)), warmup=1)
     v = bs / t
     cfg = workload(a, world)
     line = {'impl': 'reference', 'metric': METRIC, 'value': v, 'unit': 'clips/s', 'n_gpus': a.gpus,
@@ -127,7 +133,7 @@ def run_reference(a, rank, world):
             'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic', 'config': cfg,
             'cpu_baseline': {'value': v, 'unit': 'clips/s', 'cores': torch.get_num_threads(), 'kind': 'port',
                              'sample': 'median of %d train steps (fwd+CE+bwd+Adam) at batch %d clips, %s img %d, '
-                                       'torch CPU fp32' % (max(1, a.steps), bs, a.net, a.img_dim)},
+                                       'torch CPU fp32' % (max(1, min(a.steps, 5)), bs, a.net, a.img_dim)},
             'e2e': {'value': v, 'unit': 'clips/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
             'gpu_launches': 0}
     print(json.dumps(line))
@@ -281,11 +287,11 @@ def run_b200(a, rank, local_rank, world):
     cpu = None
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
         from oracle import dpc_oracle as O
-        torch.set_num_threads(os.cpu_count() or 1)
+        torch.set_num_threads(cpu_threads())
         bs = 4
-        t = O.cpu_train_step_time(a.net, a.img_dim, batch=bs, steps=5, warmup=1)
+        t = O.cpu_train_step_time(a.net, a.img_dim, batch=bs, steps=3, warmup=1)
         cpu = {'value': bs / t, 'unit': 'clips/s', 'cores': torch.get_num_threads(), 'kind': 'port',
-               'sample': 'median of 5 train steps (fwd+CE+bwd+Adam) at batch %d clips (BASELINE config 1), '
+               'sample': 'median of 3 train steps (fwd+CE+bwd+Adam) at batch %d clips (BASELINE config 1), '
                          'torch CPU fp32 oracle port' % bs}
 
     if rank == 0:

@@ -23,9 +23,9 @@ class _HeadFn(torch.autograd.Function):
     """feature rows -> score [M, M] (pool/split, ConvGRU aggregate, predictor loop, score matmul)"""
 
     @staticmethod
-    def forward(ctx, rows, dims, B, N, pred_step, dropout_p, seed, *params):
+    def forward(ctx, rows, dims, B, N, pred_step, dropout_p, seed, need, *params):
+        # `need` is decided by the caller: grad mode is always off inside Function.forward
         P = dict(zip(engine.HEAD_PARAM_NAMES, params))
-        need = torch.is_grad_enabled() and (rows.requires_grad or any(p.requires_grad for p in params))
         score, hctx = engine.head_forward(rows, dims, B, N, pred_step, P, dropout_p, seed, need_ctx=need)
         ctx.hctx = hctx
         ctx.save_for_backward(*params)
@@ -39,7 +39,7 @@ class _HeadFn(torch.autograd.Function):
         P = dict(zip(engine.HEAD_PARAM_NAMES, ctx.saved_tensors))
         drows, G = engine.head_backward(ctx.hctx, dscore.contiguous(), P)
         ctx.hctx = None
-        return (drows, None, None, None, None, None, None) + tuple(G[n] for n in engine.HEAD_PARAM_NAMES)
+        return (drows, None, None, None, None, None, None, None) + tuple(G[n] for n in engine.HEAD_PARAM_NAMES)
 
 
 class DPC_RNN(nn.Module):
@@ -94,7 +94,9 @@ class DPC_RNN(nn.Module):
         if p > 0:
             seed = (torch.initial_seed() * 0x9E3779B1 + next(_dropout_calls) * 1000003
                     + block.device.index * 7919) & 0x7FFFFFFFFFFFFFFF
-        score = _HeadFn.apply(rows, dims, B, N, self.pred_step, p, seed, *self._head_params())
+        hp = self._head_params()
+        need = torch.is_grad_enabled() and (rows.requires_grad or any(q.requires_grad for q in hp))
+        score = _HeadFn.apply(rows, dims, B, N, self.pred_step, p, seed, need, *hp)
         SQ = self.last_size ** 2
         score = score.view(B, self.pred_step, SQ, B, self.pred_step, SQ)
         if self.mask is None or self.mask.shape[0] != B or self.mask.device != block.device:

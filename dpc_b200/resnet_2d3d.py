@@ -59,9 +59,9 @@ class _BackboneFn(torch.autograd.Function):
     """x [NB,3,T,H,W] -> channels-last feature rows [NB*To*Ho*Wo, 256]"""
 
     @staticmethod
-    def forward(ctx, x, network, names, *params):
+    def forward(ctx, x, network, names, need, *params):
+        # `need` is decided by the caller: grad mode is always off inside Function.forward
         P = dict(zip(names, params))
-        need = torch.is_grad_enabled() and any(p.requires_grad for p in params)
         rows, dims, bctx = engine.backbone_forward(network, x, P, need_ctx=need)
         ctx.bctx, ctx.names = bctx, names
         ctx.save_for_backward(*params)
@@ -75,7 +75,7 @@ class _BackboneFn(torch.autograd.Function):
         P = dict(zip(ctx.names, ctx.saved_tensors))
         G = engine.backbone_backward(ctx.bctx, drows.contiguous(), P)
         ctx.bctx = None
-        return (None, None, None) + tuple(G[n] for n in ctx.names)
+        return (None, None, None, None) + tuple(G[n] for n in ctx.names)
 
 
 class ResNet2d3d_full(nn.Module):                                  # resnet_2d3d.py:205-270
@@ -154,7 +154,8 @@ class ResNet2d3d_full(nn.Module):                                  # resnet_2d3d
         x = x.contiguous().float()
         sd = dict(self.named_parameters())
         params = [sd[n].contiguous() for n in self._names]
-        rows = _BackboneFn.apply(x, self.network, self._names, *params)
+        need = torch.is_grad_enabled() and any(p.requires_grad for p in params)
+        rows = _BackboneFn.apply(x, self.network, self._names, need, *params)
         return rows, self.out_dims(x.shape[2], x.shape[3], x.shape[4])
 
     def forward(self, x):                                           # resnet_2d3d.py:259-270

@@ -52,6 +52,14 @@ def test_forward_vs_golden_and_oracle(case):
     assert [round(float(t), 5) for t in crit.topk] == [round(t, 5) for t in fx['topk']]
 
 
+# Gradients at these tiny sizes (128 rows per BN channel in layer4) are ill-conditioned in fp32: the
+# CPU oracle in fp32 differs from the same oracle in fp64 by 5.7e-3 (max) / 1.5e-3 (rel-L2) on
+# r18_img64_b2 (ReLU masks of near-zero activations flip, BN backward cancels).  So the golden check
+# uses a loose, stated bound, and test_grads_calibrated_against_fp64 bounds OUR error by the fp32
+# oracle's own error against fp64.
+GOLDEN_GRAD_TOL = 4e-2
+
+
 @pytest.mark.parametrize('case', ['r18_img64_b2', 'r34_img64_b3'])
 def test_grads_vs_golden(case):
     """loss.backward() through the unchanged driver-side loss (torch CE on our score)."""
@@ -70,8 +78,27 @@ def test_grads_vs_golden(case):
     for k, p in m.named_parameters():
         s = fx['grads'][k]
         assert p.grad is not None, k
-        worst = max(worst, check_sample(p.grad, s, GRAD_TOL, k))
+        worst = max(worst, check_sample(p.grad, s, GOLDEN_GRAD_TOL, k))
     print('worst sampled grad rel err', worst)
+
+
+def test_grads_calibrated_against_fp64():
+    """per parameter: rel-L2(ours, fp64 oracle) <= 4 x rel-L2(fp32 oracle, fp64 oracle) + 1e-3"""
+    from oracle import dpc_oracle as O
+    fx = load_fixture('r18_img64_b2')
+    sd = O.synthetic_state_dict(fx['network'], fx['seed_w'])
+    block = make_block(fx)
+    _, _, g32 = O.train_step_grads(block, sd, fx['network'], fx['pred_step'])
+    _, _, g64 = O.train_step_grads(block.double(), {k: v.double() for k, v in sd.items()}, fx['network'], fx['pred_step'])
+    m = build(fx['network'], fx['img'], fx['pred_step'], sd).eval()
+    import dpc_b200
+    score, _ = m(block.cuda())
+    dpc_b200.NCECriterion()(score).backward()
+    for k, p in m.named_parameters():
+        ref = g64[k]
+        noise = float((g32[k].double() - ref).norm() / ref.norm())
+        ours = float((p.grad.cpu().double() - ref).norm() / ref.norm())
+        assert ours <= 4 * noise + 1e-3, (k, ours, noise)
 
 
 def test_fused_criterion_grads_equal_torch_ce():
