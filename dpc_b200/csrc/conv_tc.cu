@@ -1,21 +1,21 @@
-// tcgen05 (5th-gen tensor core) implicit-GEMM for the 1x3x3 / 3x3x3 / 1x1x1 convolutions and the
-// dense score matmul, sm_100a only.
+// tcgen05 (5th-gen tensor core) implicit-GEMM kernels for the 1x3x3 / 3x3x3 / 1x1x1 convolutions
+// (forward, dgrad, wgrad; any stride) and the dense score matmul.  sm_100a only.
 //
-//   D[128 x BN] (fp32, TMEM) += sum over k-blocks  A_hi*B_hi + A_hi*B_lo + A_lo*B_hi      (3xBF16 split)
+//   D (fp32, TMEM) += sum over k-blocks  A_hi*B_hi + A_hi*B_lo + A_lo*B_hi          (3xBF16 split)
 //
 // * operands live in HBM as two bf16 planes (hi = bf16(x), lo = bf16(x - hi)): same bytes as fp32,
-//   ~16 mantissa bits, which is what the 1e-3 parity bar needs (single-pass
-//   BF16/TF32 fail it);
-// * A tile (128 output positions x 64 channels of ONE filter tap) is ONE TMA box of the channels-last
-//   activation tensor [NB,T,H,W,C] at the tap-shifted coordinate; the halo / zero padding is TMA
-//   out-of-bounds fill, so there is no im2col buffer and no index arithmetic on the SM;
-// * B tile (BN filters x 64 channels of that tap) is a TMA box of the packed weights [Co][tap][Ci];
-// * both land in shared memory in the 128B-swizzled K-major layout the UMMA descriptors expect;
+//   ~16 mantissa bits -- what the 1e-3 parity bar needs (1-pass BF16/TF32 fail it);
+// * an operand tile (positions x 64 channels of ONE filter tap) is ONE TMA box of the channels-last
+//   activation tensor [NB,T,H,W,C] at the tap-shifted coordinate; halo / zero padding is TMA
+//   out-of-bounds fill: no im2col buffer, no index arithmetic on the SM.  Strided convolutions read
+//   through per-parity views of the tensor (base pointer offset + doubled strides in the tensor map);
+// * shared-memory tiles are 128B-swizzled; forward/dgrad use K-major UMMA descriptors (K = channels),
+//   wgrad uses MN-major descriptors over the SAME boxes (K = positions);
 // * warp 0 = TMA producer, warp 1 = MMA issuer (one elected lane) + TMEM owner, warps 2-5 = epilogue
-//   (tcgen05.ld -> registers -> coalesced fp32 row stores), mbarrier full/empty ring between them.
+//   (tcgen05.ld -> registers -> global), with an mbarrier full/empty ring between them.
 //
-// Replaces nn.Conv3d at backbone/resnet_2d3d.py:13-31,241-244 (stride-1 sites; strided sites go
-// through per-parity tensor maps, see dpc_conv3d_fwd_tc) and torch.matmul at dpc/model_3d.py:83.
+// Replaces nn.Conv3d fwd/bwd at backbone/resnet_2d3d.py:13-31,241-244 and torch.matmul at
+// dpc/model_3d.py:83.
 #include "common.cuh"
 #include <cudaTypedefs.h>
 #include <cuda_bf16.h>
@@ -47,8 +47,8 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         if (done) return;
         if (clock64() - t0 > 4000000000ll) break;          // ~2 s: far beyond any legitimate wait
     }
-    printf("dpc_b200: mbarrier wait timed out (block %d,%d thread %d bar 0x%x parity %u)\n", blockIdx.x, blockIdx.y,
-           threadIdx.x, bar, parity);
+    printf("dpc_b200: mbarrier wait timed out (block %d,%d,%d thread %d bar 0x%x parity %u)\n", blockIdx.x,
+           blockIdx.y, blockIdx.z, threadIdx.x, bar, parity);
     __trap();
 }
 __device__ __forceinline__ void tma_load_5d(const CUtensorMap* map, uint32_t dst, uint32_t bar, int c0, int c1,
@@ -115,44 +115,103 @@ __device__ __forceinline__ uint64_t make_kmajor_sw128_desc(uint32_t saddr) {
     d |= (uint64_t)2 << 61;                        // SWIZZLE_128B
     return d;
 }
+// MN-major, 128B-swizzled: each smem row is one K index holding 64 contiguous MN elements (128 B);
+// 8 K-rows form a swizzle atom (SBO = 1024 B); 64-element MN groups are `lbo_bytes` apart.
+__device__ __forceinline__ uint64_t make_mnmajor_sw128_desc(uint32_t saddr, uint32_t lbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+
+// One filter-tap table entry per dimension: which original tap, which coordinate offset of the
+// gathered tensor relative to the tile origin, which parity view (strided convs).
+struct TapDim {
+    int8_t count;
+    int8_t k[3];       // original tap index along this dimension
+    int8_t off[3];     // coordinate offset
+    int8_t par[3];     // parity class (0..stride-1)
+};
+
+struct TcMaps {
+    CUtensorMap a_hi[8], a_lo[8];     // gathered tensor, one per parity view
+    CUtensorMap b_hi, b_lo;           // second operand
+};
 
 struct TcParams {
-    // filter taps: k-block kb = tap * cchunks + cc
-    int taps, kH, kW, cchunks;
-    int offT, offH, offW;      // coordinate of tap (0,0,0) relative to the output position (= -pad)
-    int Ksrc;                  // channels of A (= cchunks * 64)
-    // A box (output-position tile)
+    TapDim tT, tH, tW;
+    int kH, kW;                // full filter extents (to linearise the original tap index)
+    int sH, sW;                // strides (to linearise the parity-view index)
+    int cchunks, Ksrc;         // 64-channel chunks / channels of the gathered tensor
     int bw, bh, bt, bn, box_rows;
-    int tiles_w, tiles_h, tiles_t;
-    // output tensor extents and channel count
-    int NB, To, Ho, Wo, Co;
-    int BN, stages;
-    long long out_sn, out_st, out_sh, out_sw;    // output row index strides (rows), for strided dgrad
-    int out_t0, out_h0, out_w0;                  // output origin (parity class), rows
+    int tiles_w, tiles_h, tiles_t, tiles_n;
+    int NB, To, Ho, Wo, Co;    // extents of the tile grid and the channel count of the output
+    int BN, stages, nviews;
+    long long out_sn, out_st, out_sh, out_sw, out_base;   // output row = n*sn + t*st + h*sh + w*sw + base
+    // wgrad only
+    int taps_full, splits, ktiles_per_split;
 };
 
 constexpr int A_TILE_BYTES = 128 * 128;            // 128 rows x 64 bf16
 
-__global__ void __launch_bounds__(192, 1)
-conv_tc_kernel(const __grid_constant__ CUtensorMap mAhi, const __grid_constant__ CUtensorMap mAlo,
-               const __grid_constant__ CUtensorMap mBhi, const __grid_constant__ CUtensorMap mBlo,
-               const TcParams p, float* __restrict__ y, int accumulate) {
-    extern __shared__ __align__(1024) uint8_t smem_raw[];
-    // carve: [stage][Ahi | Alo | Bhi | Blo], then barriers
-    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-    const int b_tile_bytes = p.BN * 128;
-    const int stage_bytes = 2 * A_TILE_BYTES + 2 * b_tile_bytes;
-    const uint32_t bar_base = smem_base + p.stages * stage_bytes;      // full[s], empty[s], tmem_full, tmem_ptr
-    auto full_bar = [&](int s) { return bar_base + 8u * s; };
-    auto empty_bar = [&](int s) { return bar_base + 8u * (p.stages + s); };
-    const uint32_t tmem_full_bar = bar_base + 8u * (2 * p.stages);
-    const uint32_t tmem_ptr_addr = bar_base + 8u * (2 * p.stages + 1);
-    uint32_t* tmem_ptr_gen = reinterpret_cast<uint32_t*>(smem_raw + (tmem_ptr_addr - smem_u32(smem_raw)));
+struct SmemPlan {
+    uint32_t base, stage_bytes, b_tile_bytes, bar_base;
+    int stages;
+    __device__ uint32_t full(int s) const { return bar_base + 8u * s; }
+    __device__ uint32_t empty(int s) const { return bar_base + 8u * (stages + s); }
+    __device__ uint32_t tmem_full() const { return bar_base + 8u * (2 * stages); }
+    __device__ uint32_t tmem_ptr() const { return bar_base + 8u * (2 * stages + 1); }
+};
 
+__device__ __forceinline__ SmemPlan plan_smem(const uint8_t* smem_raw, int BN, int stages) {
+    SmemPlan s;
+    s.base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    s.b_tile_bytes = (uint32_t)BN * 128u;
+    s.stage_bytes = 2u * A_TILE_BYTES + 2u * s.b_tile_bytes;
+    s.stages = stages;
+    s.bar_base = s.base + (uint32_t)stages * s.stage_bytes;
+    return s;
+}
+
+__device__ __forceinline__ uint32_t setup_common(const SmemPlan& sp, const uint8_t* smem_raw, const TcMaps& maps,
+                                                 int nviews, uint32_t tmem_cols) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t tmem_cols = p.BN < 32 ? 32 : p.BN;     // power of two >= 32 (BN in {32,64,128,256})
+    if (warp == 0 && lane == 0) {
+        for (int v = 0; v < nviews; ++v) {
+            asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.a_hi[v]) : "memory");
+            asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.a_lo[v]) : "memory");
+        }
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.b_hi) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.b_lo) : "memory");
+        for (int s = 0; s < sp.stages; ++s) { mbar_init(sp.full(s), 1); mbar_init(sp.empty(s), 1); }
+        mbar_init(sp.tmem_full(), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) tmem_alloc(sp.tmem_ptr(), tmem_cols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    return *reinterpret_cast<const uint32_t*>(smem_raw + (sp.tmem_ptr() - smem_u32(smem_raw)));
+}
 
-    // tile coordinates
+// =============================================================================================
+// forward / dgrad / plain GEMM:  out[position, co] = sum_{tap, c} G[position (+) tap, c] * Wp[co][tap][c]
+// =============================================================================================
+__global__ void __launch_bounds__(192, 1)
+conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p, float* __restrict__ y, int accumulate) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    const SmemPlan sp = plan_smem(smem_raw, p.BN, p.stages);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // Two accumulators: columns [0,BN) take hi*hi, [BN,2BN) the two cross terms.  The TMEM accumulate
+    // truncates (measured: mean relative error -2e-8 per accumulation step), so keeping the small terms
+    // out of the main chain cuts that bias 3x; the epilogue adds the two in fp32 (round-to-nearest).
+    const uint32_t tmem_cols = 2u * (p.BN < 16 ? 16 : p.BN);
+    const uint32_t tmem_d = setup_common(sp, smem_raw, maps, p.nviews, tmem_cols);
+    const uint32_t tmem_c = tmem_d + (uint32_t)p.BN;
+
     int tile = blockIdx.x;
     const int tw = tile % p.tiles_w; tile /= p.tiles_w;
     const int th = tile % p.tiles_h; tile /= p.tiles_h;
@@ -160,84 +219,73 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mAhi, const __grid_constant__
     const int tn = tile;
     const int w0 = tw * p.bw, h0 = th * p.bh, t0 = tt * p.bt, n0 = tn * p.bn;
     const int ncol0 = blockIdx.y * p.BN;
-    const int num_kb = p.taps * p.cchunks;
-
-    if (warp == 0 && lane == 0) {
-        asm volatile("prefetch.tensormap [%0];" ::"l"(&mAhi) : "memory");
-        asm volatile("prefetch.tensormap [%0];" ::"l"(&mAlo) : "memory");
-        asm volatile("prefetch.tensormap [%0];" ::"l"(&mBhi) : "memory");
-        asm volatile("prefetch.tensormap [%0];" ::"l"(&mBlo) : "memory");
-        for (int s = 0; s < p.stages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-        mbar_init(tmem_full_bar, 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    if (warp == 1) tmem_alloc(tmem_ptr_addr, tmem_cols);
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem_d = *tmem_ptr_gen;
+    const int ntaps = p.tT.count * p.tH.count * p.tW.count;
+    const int num_kb = ntaps * p.cchunks;
 
     if (warp == 0) {
-        // ===== TMA producer =====
         if (elect_one()) {
-            const uint32_t tx = 2u * (uint32_t)(p.box_rows * 128) + 2u * (uint32_t)b_tile_bytes;
+            const uint32_t tx = 2u * (uint32_t)(p.box_rows * 128) + 2u * sp.b_tile_bytes;
             int s = 0; uint32_t ph = 0;
             for (int kb = 0; kb < num_kb; ++kb) {
                 const int tap = kb / p.cchunks, cc = kb - tap * p.cchunks;
-                const int kt = tap / (p.kH * p.kW), kh = (tap / p.kW) % p.kH, kw = tap % p.kW;
-                mbar_wait(empty_bar(s), ph ^ 1u);
-                mbar_expect_tx(full_bar(s), tx);
-                const uint32_t sa = smem_base + s * stage_bytes;
-                const int cw = w0 + kw + p.offW, chh = h0 + kh + p.offH, ct = t0 + kt + p.offT;
-                tma_load_5d(&mAhi, sa, full_bar(s), cc * 64, cw, chh, ct, n0);
-                tma_load_5d(&mAlo, sa + A_TILE_BYTES, full_bar(s), cc * 64, cw, chh, ct, n0);
-                const int kcol = tap * p.Ksrc + cc * 64;
-                tma_load_2d(&mBhi, sa + 2 * A_TILE_BYTES, full_bar(s), kcol, ncol0);
-                tma_load_2d(&mBlo, sa + 2 * A_TILE_BYTES + b_tile_bytes, full_bar(s), kcol, ncol0);
+                const int iw = tap % p.tW.count, ih = (tap / p.tW.count) % p.tH.count, it = tap / (p.tW.count * p.tH.count);
+                const int tap_full = (p.tT.k[it] * p.kH + p.tH.k[ih]) * p.kW + p.tW.k[iw];
+                const int view = (p.tT.par[it] * p.sH + p.tH.par[ih]) * p.sW + p.tW.par[iw];
+                mbar_wait(sp.empty(s), ph ^ 1u);
+                mbar_expect_tx(sp.full(s), tx);
+                const uint32_t sa = sp.base + s * sp.stage_bytes;
+                const int cw = w0 + p.tW.off[iw], chh = h0 + p.tH.off[ih], ct = t0 + p.tT.off[it];
+                tma_load_5d(&maps.a_hi[view], sa, sp.full(s), cc * 64, cw, chh, ct, n0);
+                tma_load_5d(&maps.a_lo[view], sa + A_TILE_BYTES, sp.full(s), cc * 64, cw, chh, ct, n0);
+                const int kcol = tap_full * p.Ksrc + cc * 64;
+                tma_load_2d(&maps.b_hi, sa + 2 * A_TILE_BYTES, sp.full(s), kcol, ncol0);
+                tma_load_2d(&maps.b_lo, sa + 2 * A_TILE_BYTES + sp.b_tile_bytes, sp.full(s), kcol, ncol0);
                 if (++s == p.stages) { s = 0; ph ^= 1u; }
             }
         }
     } else if (warp == 1) {
-        // ===== MMA issuer =====
         if (elect_one()) {
             // instruction descriptor: D=f32, A=B=bf16, both K-major, N = BN, M = 128
             const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.BN >> 3) << 17) | ((128u >> 4) << 24);
             int s = 0; uint32_t ph = 0;
             for (int kb = 0; kb < num_kb; ++kb) {
-                mbar_wait(full_bar(s), ph);
+                mbar_wait(sp.full(s), ph);
                 tc_fence_after();
-                const uint32_t sa = smem_base + s * stage_bytes;
+                const uint32_t sa = sp.base + s * sp.stage_bytes;
                 const uint64_t ahi = make_kmajor_sw128_desc(sa), alo = make_kmajor_sw128_desc(sa + A_TILE_BYTES);
                 const uint64_t bhi = make_kmajor_sw128_desc(sa + 2 * A_TILE_BYTES);
-                const uint64_t blo = make_kmajor_sw128_desc(sa + 2 * A_TILE_BYTES + b_tile_bytes);
+                const uint64_t blo = make_kmajor_sw128_desc(sa + 2 * A_TILE_BYTES + sp.b_tile_bytes);
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {               // 4 x UMMA_K(16) = 64 channels; +32 B per step
                     const uint64_t ko = (uint64_t)(k * 2);
                     umma_bf16(tmem_d, ahi + ko, bhi + ko, idesc, (kb | k) ? 1u : 0u);
-                    umma_bf16(tmem_d, ahi + ko, blo + ko, idesc, 1u);
-                    umma_bf16(tmem_d, alo + ko, bhi + ko, idesc, 1u);
+                    umma_bf16(tmem_c, ahi + ko, blo + ko, idesc, (kb | k) ? 1u : 0u);
+                    umma_bf16(tmem_c, alo + ko, bhi + ko, idesc, 1u);
                 }
-                umma_commit(empty_bar(s));                  // frees the smem stage when these MMAs retire
+                umma_commit(sp.empty(s));                   // frees the smem stage when these MMAs retire
                 if (++s == p.stages) { s = 0; ph ^= 1u; }
             }
-            umma_commit(tmem_full_bar);                     // accumulator complete
+            umma_commit(sp.tmem_full());
         }
     } else {
-        // ===== epilogue: warps 2..5; TMEM lane quarter = warp % 4 =====
+        // epilogue: warps 2..5; TMEM lane quarter = warp % 4
         const int q = warp & 3;
-        const int r = q * 32 + lane;                        // tile row == TMEM lane
+        const int r = q * 32 + lane;
         const int dw = r % p.bw, dh = (r / p.bw) % p.bh, dt = (r / (p.bw * p.bh)) % p.bt, dn = r / (p.bw * p.bh * p.bt);
         const int n = n0 + dn, t = t0 + dt, h = h0 + dh, w = w0 + dw;
         const bool valid = r < p.box_rows && n < p.NB && t < p.To && h < p.Ho && w < p.Wo;
-        const long long row = (long long)n * p.out_sn + (long long)(t + p.out_t0) * p.out_st +
-                              (long long)(h + p.out_h0) * p.out_sh + (long long)(w + p.out_w0) * p.out_sw;
+        const long long row = (long long)n * p.out_sn + (long long)t * p.out_st + (long long)h * p.out_sh +
+                              (long long)w * p.out_sw + p.out_base;
         float* yrow = y + row * p.Co + ncol0;
-        mbar_wait(tmem_full_bar, 0);
+        mbar_wait(sp.tmem_full(), 0);
         tc_fence_after();
         const bool vec = (p.Co & 3) == 0;
         for (int c0 = 0; c0 < p.BN; c0 += 32) {
-            uint32_t v[32];
+            uint32_t v[32], u[32];
             tmem_ld32(tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+            tmem_ld32(tmem_c + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, u);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(u[j]));
             if (!valid) continue;
             if (vec && ncol0 + c0 + 32 <= p.Co) {
 #pragma unroll
@@ -265,6 +313,124 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mAhi, const __grid_constant__
     if (warp == 1) tmem_dealloc(tmem_d, tmem_cols);
 }
 
+// =============================================================================================
+// wgrad:  dW[co][tap][ci] += sum_{positions} dY[pos, co] * X[pos (+) tap, ci]
+//   A = dY^T (M = co, K = positions), B = X^T (N = ci, K = positions): both MN-major over the
+//   same [positions x 64 channels] TMA boxes.  grid = (co tiles * ci tiles, taps, splits);
+//   partial sums are reduced with fp32 atomics.
+// =============================================================================================
+__global__ void __launch_bounds__(192, 1)
+wgrad_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p, float* __restrict__ dwp) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    const SmemPlan sp = plan_smem(smem_raw, p.BN, p.stages);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t tmem_cols = 2u * (p.BN < 16 ? 16 : p.BN);   // main + correction accumulators
+    // Position boxes may hold fewer than a multiple of 16 rows (UMMA_K): rows the TMA never writes
+    // must read as zero, so clear the operand stages once (generic proxy), then hand over to the
+    // async proxy (TMA / UMMA).
+    {
+        uint4* z = reinterpret_cast<uint4*>(smem_raw + (sp.base - smem_u32(smem_raw)));
+        const int n16 = (int)((uint32_t)sp.stages * sp.stage_bytes / 16u);
+        for (int i = threadIdx.x; i < n16; i += blockDim.x) z[i] = make_uint4(0u, 0u, 0u, 0u);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    const uint32_t tmem_d = setup_common(sp, smem_raw, maps, p.nviews, tmem_cols);
+    const uint32_t tmem_c = tmem_d + (uint32_t)p.BN;
+
+    const int ci_tiles = (p.Ksrc + p.BN - 1) / p.BN;
+    const int co0 = (blockIdx.x / ci_tiles) * 128, ci0 = (blockIdx.x % ci_tiles) * p.BN;
+    // this CTA's tap
+    const int tap = blockIdx.y;
+    const int iw = tap % p.tW.count, ih = (tap / p.tW.count) % p.tH.count, it = tap / (p.tW.count * p.tH.count);
+    const int tap_full = (p.tT.k[it] * p.kH + p.tH.k[ih]) * p.kW + p.tW.k[iw];
+    const int view = (p.tT.par[it] * p.sH + p.tH.par[ih]) * p.sW + p.tW.par[iw];
+    const int total_tiles = p.tiles_w * p.tiles_h * p.tiles_t * p.tiles_n;
+    const int kt_beg = blockIdx.z * p.ktiles_per_split;
+    int kt_end = kt_beg + p.ktiles_per_split;
+    if (kt_end > total_tiles) kt_end = total_tiles;
+    const int num_kb = kt_end - kt_beg;
+    const int nb_groups = p.BN / 64;              // 64-channel groups of the B operand
+    const uint32_t box_bytes = (uint32_t)p.box_rows * 128u;   // one [positions x 64ch] box (<= 8 KB)
+    const uint32_t GROUP = 8192u;                 // smem distance between 64-channel groups (64 rows * 128 B)
+
+    if (num_kb > 0) {
+        if (warp == 0) {
+            if (elect_one()) {
+                const uint32_t tx = 2u * 2u * box_bytes + 2u * (uint32_t)nb_groups * box_bytes;
+                int s = 0; uint32_t ph = 0;
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    int tile = kt_beg + kb;
+                    const int tw = tile % p.tiles_w; tile /= p.tiles_w;
+                    const int th = tile % p.tiles_h; tile /= p.tiles_h;
+                    const int tt = tile % p.tiles_t; tile /= p.tiles_t;
+                    const int w0 = tw * p.bw, h0 = th * p.bh, t0 = tt * p.bt, n0 = tile * p.bn;
+                    mbar_wait(sp.empty(s), ph ^ 1u);
+                    mbar_expect_tx(sp.full(s), tx);
+                    const uint32_t sa = sp.base + s * sp.stage_bytes;
+                    // A = dY at the output positions (dense map = maps.b_*, 5-D), two 64-channel groups
+                    for (int g = 0; g < 2; ++g) {
+                        tma_load_5d(&maps.b_hi, sa + g * GROUP, sp.full(s), co0 + g * 64, w0, h0, t0, n0);
+                        tma_load_5d(&maps.b_lo, sa + A_TILE_BYTES + g * GROUP, sp.full(s), co0 + g * 64, w0, h0, t0, n0);
+                    }
+                    // B = X at the tap-shifted positions (parity view)
+                    const int cw = w0 + p.tW.off[iw], chh = h0 + p.tH.off[ih], ct = t0 + p.tT.off[it];
+                    for (int g = 0; g < nb_groups; ++g) {
+                        tma_load_5d(&maps.a_hi[view], sa + 2 * A_TILE_BYTES + g * GROUP, sp.full(s), ci0 + g * 64, cw, chh, ct, n0);
+                        tma_load_5d(&maps.a_lo[view], sa + 2 * A_TILE_BYTES + sp.b_tile_bytes + g * GROUP, sp.full(s),
+                                    ci0 + g * 64, cw, chh, ct, n0);
+                    }
+                    if (++s == p.stages) { s = 0; ph ^= 1u; }
+                }
+            }
+        } else if (warp == 1) {
+            if (elect_one()) {
+                // D=f32, A=B=bf16, both MN-major (bits 15,16), N = BN, M = 128
+                const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) |
+                                       ((uint32_t)(p.BN >> 3) << 17) | ((128u >> 4) << 24);
+                const int ksteps = (p.box_rows + 15) / 16;  // UMMA_K = 16 positions; rows past the box are zero
+                int s = 0; uint32_t ph = 0;
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    mbar_wait(sp.full(s), ph);
+                    tc_fence_after();
+                    const uint32_t sa = sp.base + s * sp.stage_bytes;
+                    const uint64_t ahi = make_mnmajor_sw128_desc(sa, GROUP), alo = make_mnmajor_sw128_desc(sa + A_TILE_BYTES, GROUP);
+                    const uint64_t bhi = make_mnmajor_sw128_desc(sa + 2 * A_TILE_BYTES, GROUP);
+                    const uint64_t blo = make_mnmajor_sw128_desc(sa + 2 * A_TILE_BYTES + sp.b_tile_bytes, GROUP);
+                    for (int k = 0; k < ksteps; ++k) {          // 16 positions = 2 swizzle atoms = 2048 B
+                        const uint64_t ko = (uint64_t)(k * (2048 >> 4));
+                        umma_bf16(tmem_d, ahi + ko, bhi + ko, idesc, (kb | k) ? 1u : 0u);
+                        umma_bf16(tmem_c, ahi + ko, blo + ko, idesc, (kb | k) ? 1u : 0u);
+                        umma_bf16(tmem_c, alo + ko, bhi + ko, idesc, 1u);
+                    }
+                    umma_commit(sp.empty(s));
+                    if (++s == p.stages) { s = 0; ph ^= 1u; }
+                }
+                umma_commit(sp.tmem_full());
+            }
+        } else {
+            const int q = warp & 3;
+            const int co = co0 + q * 32 + lane;             // D row = output channel
+            mbar_wait(sp.tmem_full(), 0);
+            tc_fence_after();
+            float* orow = dwp + ((size_t)co * p.taps_full + tap_full) * p.Ksrc + ci0;
+            for (int c0 = 0; c0 < p.BN; c0 += 32) {
+                uint32_t v[32], u[32];
+                tmem_ld32(tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+                tmem_ld32(tmem_c + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, u);
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(u[j]));
+                if (co >= p.Co) continue;
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                    if (ci0 + c0 + j < p.Ksrc) atomicAdd(orow + c0 + j, __uint_as_float(v[j]));
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_d, tmem_cols);
+}
+
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
@@ -280,7 +446,7 @@ PFN_cuTensorMapEncodeTiled_v12000 get_encode() {
     return fn;
 }
 
-// bf16 tensor [d4][d3][d2][d1][d0] (d0 contiguous) with arbitrary byte strides for d1..d4
+// bf16 tensor, dims[0] contiguous, arbitrary byte strides for the outer dims
 int make_map(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
              const uint32_t* box) {
     auto enc = get_encode();
@@ -293,19 +459,19 @@ int make_map(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, c
     CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gd, gs, bx, es,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    DPC_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (%d) rank %d dims %llu %llu box %u %u", (int)r, rank,
-                (unsigned long long)dims[0], (unsigned long long)dims[1], box[0], box[1]);
+    DPC_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (%d) rank %d dims %llu %llu %llu box %u %u %u", (int)r,
+                rank, (unsigned long long)dims[0], (unsigned long long)dims[1], (unsigned long long)(rank > 2 ? dims[2] : 0),
+                box[0], box[1], rank > 2 ? box[2] : 0);
     return DPC_OK;
 }
 
-// pick the box (bw,bh,bt,bn), product <= 128, maximising coverage efficiency per dimension
-// Every tile costs a full 128-row MMA, so minimise the tile count; ties -> longer contiguous rows.
-void choose_box(int W, int H, int T, int NB, int& bw, int& bh, int& bt, int& bn) {
+// Every tile costs a full MMA of `rows_max` rows, so minimise the tile count; ties -> longer rows.
+void choose_box(int W, int H, int T, int NB, int rows_max, int& bw, int& bh, int& bt, int& bn) {
     auto cdiv = [](long long a, long long b) { return (a + b - 1) / b; };
     long long best = -1;
     bw = bh = bt = bn = 1;
-    for (int w = (W < 128 ? W : 128); w >= 1; --w) {
-        const int rh = 128 / w;
+    for (int w = (W < rows_max ? W : rows_max); w >= 1; --w) {
+        const int rh = rows_max / w;
         for (int h = (H < rh ? H : rh); h >= 1; --h) {
             const int rt = rh / h;
             for (int t = (T < rt ? T : rt); t >= 1; --t) {
@@ -320,57 +486,101 @@ void choose_box(int W, int H, int T, int NB, int& bw, int& bh, int& bt, int& bn)
 
 struct TcLaunch {
     TcParams p;
-    CUtensorMap mAhi, mAlo, mBhi, mBlo;
+    TcMaps maps;
     dim3 grid;
     size_t smem;
 };
 
-// A: bf16 planes of a channels-last tensor with extents (NB, Ta, Ha, Wa, Ca) and row strides
-// (in elements) sn, st, sh, sw (sw = Ca for a dense tensor; parity views use multiples).
-int setup(TcLaunch& L, const void* a_hi, const void* a_lo, int NB, int Ta, int Ha, int Wa, int Ca,
-          long long sn, long long st, long long sh, long long sw,
-          const void* b_hi, const void* b_lo, int Co, int Ktot,
-          int To, int Ho, int Wo, int taps, int kH, int kW, int offT, int offH, int offW) {
+// 5-D map over (a parity view of) a channels-last bf16 tensor [NB,T,H,W,C]
+int make_act_map(CUtensorMap* m, const void* base, int C, int W, int H, int T, int NB, long long sw, long long sh,
+                 long long st, long long sn, const uint32_t* box) {
+    const uint64_t d[5] = {(uint64_t)C, (uint64_t)W, (uint64_t)H, (uint64_t)T, (uint64_t)NB};
+    const uint64_t s[4] = {(uint64_t)sw * 2, (uint64_t)sh * 2, (uint64_t)st * 2, (uint64_t)sn * 2};
+    return make_map(m, base, 5, d, s, box);
+}
+
+void set_stages(TcLaunch& L, int num_kb) {
     TcParams& p = L.p;
-    DPC_REQUIRE(Ca % 64 == 0, "tcgen05 conv: channel count %d must be a multiple of 64", Ca);
-    p.taps = taps; p.kH = kH; p.kW = kW; p.cchunks = Ca / 64; p.Ksrc = Ca;
-    p.offT = offT; p.offH = offH; p.offW = offW;
-    choose_box(Wo, Ho, To, NB, p.bw, p.bh, p.bt, p.bn);
-    p.box_rows = p.bw * p.bh * p.bt * p.bn;
-    p.tiles_w = (Wo + p.bw - 1) / p.bw; p.tiles_h = (Ho + p.bh - 1) / p.bh; p.tiles_t = (To + p.bt - 1) / p.bt;
-    const int tiles_n = (NB + p.bn - 1) / p.bn;
-    p.NB = NB; p.To = To; p.Ho = Ho; p.Wo = Wo; p.Co = Co;
-    p.BN = Co >= 256 ? 256 : (Co >= 128 ? 128 : (Co >= 64 ? 64 : 32));
     const int stage_bytes = 2 * A_TILE_BYTES + 2 * p.BN * 128;
     int stages = (200 * 1024) / stage_bytes;
     if (stages > 6) stages = 6;
-    const int num_kb = taps * p.cchunks;
     if (stages > num_kb) stages = num_kb;
-    DPC_REQUIRE(stages >= 1, "tcgen05 conv: no pipeline stage fits");
+    if (stages < 1) stages = 1;
     p.stages = stages;
     L.smem = (size_t)stages * stage_bytes + 8 * (2 * stages + 2) + 1024;
-    // default: dense output [NB,To,Ho,Wo]
-    p.out_sw = 1; p.out_sh = Wo; p.out_st = (long long)Ho * Wo; p.out_sn = (long long)To * Ho * Wo;
-    p.out_t0 = p.out_h0 = p.out_w0 = 0;
-    const uint64_t ad[5] = {(uint64_t)Ca, (uint64_t)Wa, (uint64_t)Ha, (uint64_t)Ta, (uint64_t)NB};
-    const uint64_t as[4] = {(uint64_t)sw * 2, (uint64_t)sh * 2, (uint64_t)st * 2, (uint64_t)sn * 2};
-    const uint32_t ab[5] = {64, (uint32_t)p.bw, (uint32_t)p.bh, (uint32_t)p.bt, (uint32_t)p.bn};
-    if (int rc = make_map(&L.mAhi, a_hi, 5, ad, as, ab)) return rc;
-    if (int rc = make_map(&L.mAlo, a_lo, 5, ad, as, ab)) return rc;
-    const uint64_t bd[2] = {(uint64_t)Ktot, (uint64_t)Co};
-    const uint64_t bs[1] = {(uint64_t)Ktot * 2};
-    const uint32_t bb[2] = {64, (uint32_t)p.BN};
-    if (int rc = make_map(&L.mBhi, b_hi, 2, bd, bs, bb)) return rc;
-    if (int rc = make_map(&L.mBlo, b_lo, 2, bd, bs, bb)) return rc;
-    L.grid = dim3((unsigned)(p.tiles_w * p.tiles_h * p.tiles_t * tiles_n), (unsigned)((Co + p.BN - 1) / p.BN));
+}
+
+int pick_bn(int C) { return C >= 256 ? 256 : (C >= 128 ? 128 : (C >= 64 ? 64 : 32)); }
+
+// forward tap tables for one dimension: input coord = s*o + k - p = s*(o + off) + par
+void fwd_taps(TapDim& d, int K, int s, int pad) {
+    d.count = (int8_t)K;
+    for (int k = 0; k < K; ++k) {
+        int par = ((k - pad) % s + s) % s;
+        d.k[k] = (int8_t)k;
+        d.par[k] = (int8_t)par;
+        d.off[k] = (int8_t)((k - pad - par) / s);
+    }
+}
+// dgrad tap tables for output parity class `cls`: taps k = (cls+pad) mod s, +s, ...; dy coord = j + (cls+pad-k)/s
+void dgrad_taps(TapDim& d, int K, int s, int pad, int cls) {
+    int n = 0;
+    for (int k = (cls + pad) % s; k < K; k += s) {
+        d.k[n] = (int8_t)k;
+        d.par[n] = 0;
+        d.off[n] = (int8_t)((cls + pad - k) / s);
+        ++n;
+    }
+    d.count = (int8_t)n;
+}
+
+int check_geom(const dpc_conv_geom* g, const char* who) {
+    DPC_REQUIRE(g != nullptr, "%s: null geometry", who);
+    DPC_REQUIRE(g->kT >= 1 && g->kT <= 3 && g->kH >= 1 && g->kH <= 3 && g->kW >= 1 && g->kW <= 3,
+                "%s: filter extents must be 1..3", who);
+    DPC_REQUIRE(g->sT >= 1 && g->sT <= 2 && g->sH >= 1 && g->sH <= 2 && g->sW >= 1 && g->sW <= 2,
+                "%s: strides must be 1 or 2", who);
+    DPC_REQUIRE(g->Ci % 64 == 0 && g->Co % 64 == 0, "%s: Ci (%d) and Co (%d) must be multiples of 64", who, g->Ci, g->Co);
+    DPC_REQUIRE((g->Ti + 2 * g->pT - g->kT) / g->sT + 1 == g->To && (g->Hi + 2 * g->pH - g->kH) / g->sH + 1 == g->Ho &&
+                    (g->Wi + 2 * g->pW - g->kW) / g->sW + 1 == g->Wo,
+                "%s: output extent does not match the conv arithmetic", who);
     return DPC_OK;
 }
 
-int launch(TcLaunch& L, float* y, int accumulate, cudaStream_t st) {
+// parity views of x [NB,Ti,Hi,Wi,Ci] for a conv with strides (sT,sH,sW)
+int make_parity_views(TcMaps& maps, const dpc_conv_geom* g, const void* x_hi, const void* x_lo, const uint32_t* box) {
+    const long long sw = g->Ci, sh = (long long)g->Wi * sw, st = (long long)g->Hi * sh, sn = (long long)g->Ti * st;
+    for (int pt = 0; pt < g->sT; ++pt)
+        for (int ph = 0; ph < g->sH; ++ph)
+            for (int pw = 0; pw < g->sW; ++pw) {
+                const int v = (pt * g->sH + ph) * g->sW + pw;
+                const int Tv = (g->Ti - pt + g->sT - 1) / g->sT, Hv = (g->Hi - ph + g->sH - 1) / g->sH,
+                          Wv = (g->Wi - pw + g->sW - 1) / g->sW;
+                DPC_REQUIRE(Tv > 0 && Hv > 0 && Wv > 0, "parity view is empty");
+                const long long off = (pt * st + ph * sh + pw * sw) * 2;   // bytes
+                if (int rc = make_act_map(&maps.a_hi[v], (const char*)x_hi + off, g->Ci, Wv, Hv, Tv, g->NB, sw * g->sW,
+                                          sh * g->sH, st * g->sT, sn, box))
+                    return rc;
+                if (int rc = make_act_map(&maps.a_lo[v], (const char*)x_lo + off, g->Ci, Wv, Hv, Tv, g->NB, sw * g->sW,
+                                          sh * g->sH, st * g->sT, sn, box))
+                    return rc;
+            }
+    return DPC_OK;
+}
+
+int launch_conv(TcLaunch& L, float* y, int accumulate, cudaStream_t st) {
     DPC_CUDA(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smem));
-    conv_tc_kernel<<<L.grid, 192, L.smem, st>>>(L.mAhi, L.mAlo, L.mBhi, L.mBlo, L.p, y, accumulate);
+    conv_tc_kernel<<<L.grid, 192, L.smem, st>>>(L.maps, L.p, y, accumulate);
     DPC_LAUNCH_CHECK();
     return DPC_OK;
+}
+
+void set_tile_grid(TcParams& p, int NB, int T, int H, int W, int rows_max) {
+    choose_box(W, H, T, NB, rows_max, p.bw, p.bh, p.bt, p.bn);
+    p.box_rows = p.bw * p.bh * p.bt * p.bn;
+    p.tiles_w = (W + p.bw - 1) / p.bw; p.tiles_h = (H + p.bh - 1) / p.bh; p.tiles_t = (T + p.bt - 1) / p.bt;
+    p.tiles_n = (NB + p.bn - 1) / p.bn;
+    p.NB = NB; p.To = T; p.Ho = H; p.Wo = W;
 }
 
 __global__ void split_bf16_kernel(const float4* __restrict__ src, uint2* __restrict__ hi, uint2* __restrict__ lo,
@@ -391,13 +601,12 @@ __global__ void split_bf16_kernel(const float4* __restrict__ src, uint2* __restr
     }
 }
 
-// w [Co][Ci][taps] fp32 -> forward planes [Co][tap][Ci] and dgrad planes [Ci][tap'][Co] (tap' = flipped)
+// w [Co][Ci][taps] fp32 -> forward planes [Co][tap][Ci] and dgrad planes [Ci][tap][Co]
 __global__ void pack_weight_bf16_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ fh,
                                         __nv_bfloat16* __restrict__ fl, __nv_bfloat16* __restrict__ dh,
                                         __nv_bfloat16* __restrict__ dl, int Co, int Ci, int taps) {
     long long total = (long long)Co * Ci * taps;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        // i indexes the forward layout [co][tap][ci]
         int ci = (int)(i % Ci);
         int tap = (int)((i / Ci) % taps);
         int co = (int)(i / ((long long)Ci * taps));
@@ -406,9 +615,20 @@ __global__ void pack_weight_bf16_kernel(const float* __restrict__ w, __nv_bfloat
         __nv_bfloat16 l = __float2bfloat16_rn(v - __bfloat162float(h));
         if (fh) { fh[i] = h; fl[i] = l; }
         if (dh) {
-            size_t j = ((size_t)ci * taps + (taps - 1 - tap)) * Co + co;
+            size_t j = ((size_t)ci * taps + tap) * Co + co;
             dh[j] = h; dl[j] = l;
         }
+    }
+}
+
+// dwp [Co][tap][Ci] -> dw [Co][Ci][tap]
+__global__ void unpack_wgrad_ctc_kernel(const float* __restrict__ dwp, float* __restrict__ dw, int Co, int Ci, int taps) {
+    long long total = (long long)Co * Ci * taps;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        int ci = (int)(i % Ci);
+        int tap = (int)((i / Ci) % taps);
+        int co = (int)(i / ((long long)Ci * taps));
+        dw[((size_t)co * Ci + ci) * taps + tap] = dwp[i];
     }
 }
 
@@ -438,33 +658,153 @@ extern "C" int dpc_pack_conv_weight_bf16(const float* w, void* wf_hi, void* wf_l
     return DPC_OK;
 }
 
-// C[M,N] (fp32, ldc = N) = A[M,K] * B[N,K]^T from split-bf16 planes (K % 64 == 0)
+// C[M,N] (fp32, ldc = N) (+)= A[M,K] * B[N,K]^T from split-bf16 planes (K % 64 == 0)
 extern "C" int dpc_gemm_nt_bf16x3_tc(int M, int N, int K, const void* a_hi, const void* a_lo, const void* b_hi,
-                                     const void* b_lo, float* C, void* stream) {
+                                     const void* b_lo, float* C, int accumulate, void* stream) {
     DPC_REQUIRE(M > 0 && N > 0 && K > 0 && K % 64 == 0, "dpc_gemm_nt_bf16x3_tc: bad dims %d %d %d", M, N, K);
     DPC_REQUIRE(a_hi && a_lo && b_hi && b_lo && C, "dpc_gemm_nt_bf16x3_tc: null pointer");
     TcLaunch L;
-    // a [1,1,1,M,K] "image" convolved with a 1x1x1 filter bank of N filters
-    if (int rc = setup(L, a_hi, a_lo, 1, 1, 1, M, K, (long long)M * K, (long long)M * K, (long long)M * K, K, b_hi, b_lo,
-                       N, K, 1, 1, M, 1, 1, 1, 0, 0, 0))
-        return rc;
-    return launch(L, C, 0, as_stream(stream));
+    memset(&L.p, 0, sizeof(L.p));
+    TcParams& p = L.p;
+    // A is a [1,1,1,M,K] "image" convolved with a 1x1x1 bank of N filters
+    fwd_taps(p.tT, 1, 1, 0); fwd_taps(p.tH, 1, 1, 0); fwd_taps(p.tW, 1, 1, 0);
+    p.kH = p.kW = 1; p.sH = p.sW = 1; p.nviews = 1;
+    p.cchunks = K / 64; p.Ksrc = K;
+    set_tile_grid(p, 1, 1, 1, M, 128);
+    p.Co = N; p.BN = pick_bn(N);
+    set_stages(L, p.cchunks);
+    p.out_sw = 1; p.out_sh = M; p.out_st = M; p.out_sn = M; p.out_base = 0;
+    const uint32_t box[5] = {64, (uint32_t)p.bw, 1, 1, 1};
+    const long long mk = (long long)M * K;
+    if (int rc = make_act_map(&L.maps.a_hi[0], a_hi, K, M, 1, 1, 1, K, mk, mk, mk, box)) return rc;
+    if (int rc = make_act_map(&L.maps.a_lo[0], a_lo, K, M, 1, 1, 1, K, mk, mk, mk, box)) return rc;
+    const uint64_t bd[2] = {(uint64_t)K, (uint64_t)N};
+    const uint64_t bs[1] = {(uint64_t)K * 2};
+    const uint32_t bb[2] = {64, (uint32_t)p.BN};
+    if (int rc = make_map(&L.maps.b_hi, b_hi, 2, bd, bs, bb)) return rc;
+    if (int rc = make_map(&L.maps.b_lo, b_lo, 2, bd, bs, bb)) return rc;
+    L.grid = dim3((unsigned)(p.tiles_w), (unsigned)((N + p.BN - 1) / p.BN));
+    return launch_conv(L, C, accumulate, as_stream(stream));
 }
 
-// stride-1 convolution (forward, or dgrad when called with dy planes and flipped/transposed weights):
-// y [NB,To,Ho,Wo,Co] (+)= conv(x planes [NB,Ti,Hi,Wi,Ci], w planes [Co][taps][Ci])
-extern "C" int dpc_conv3d_s1_tc(const dpc_conv_geom* g, const void* x_hi, const void* x_lo, const void* w_hi,
-                                const void* w_lo, float* y, int accumulate, void* stream) {
-    DPC_REQUIRE(g && x_hi && x_lo && w_hi && w_lo && y, "dpc_conv3d_s1_tc: null pointer");
-    DPC_REQUIRE(g->sT == 1 && g->sH == 1 && g->sW == 1, "dpc_conv3d_s1_tc: stride must be 1");
-    DPC_REQUIRE((g->Ti + 2 * g->pT - g->kT) + 1 == g->To && (g->Hi + 2 * g->pH - g->kH) + 1 == g->Ho &&
-                    (g->Wi + 2 * g->pW - g->kW) + 1 == g->Wo,
-                "dpc_conv3d_s1_tc: output extent does not match the conv arithmetic");
+// forward conv, any stride in {1,2}: y [NB,To,Ho,Wo,Co] = conv(x planes [NB,Ti,Hi,Wi,Ci], wf planes [Co][taps][Ci])
+extern "C" int dpc_conv3d_fwd_tc(const dpc_conv_geom* g, const void* x_hi, const void* x_lo, const void* wf_hi,
+                                 const void* wf_lo, float* y, void* stream) {
+    if (int rc = check_geom(g, "dpc_conv3d_fwd_tc")) return rc;
+    DPC_REQUIRE(x_hi && x_lo && wf_hi && wf_lo && y, "dpc_conv3d_fwd_tc: null pointer");
+    TcLaunch L;
+    memset(&L.p, 0, sizeof(L.p));
+    TcParams& p = L.p;
+    fwd_taps(p.tT, g->kT, g->sT, g->pT); fwd_taps(p.tH, g->kH, g->sH, g->pH); fwd_taps(p.tW, g->kW, g->sW, g->pW);
+    p.kH = g->kH; p.kW = g->kW; p.sH = g->sH; p.sW = g->sW; p.nviews = g->sT * g->sH * g->sW;
+    p.cchunks = g->Ci / 64; p.Ksrc = g->Ci;
+    set_tile_grid(p, g->NB, g->To, g->Ho, g->Wo, 128);
+    p.Co = g->Co; p.BN = pick_bn(g->Co);
+    const int taps = g->kT * g->kH * g->kW;
+    set_stages(L, taps * p.cchunks);
+    p.out_sw = 1; p.out_sh = g->Wo; p.out_st = (long long)g->Ho * g->Wo; p.out_sn = (long long)g->To * g->Ho * g->Wo;
+    p.out_base = 0;
+    const uint32_t box[5] = {64, (uint32_t)p.bw, (uint32_t)p.bh, (uint32_t)p.bt, (uint32_t)p.bn};
+    if (int rc = make_parity_views(L.maps, g, x_hi, x_lo, box)) return rc;
+    const uint64_t bd[2] = {(uint64_t)taps * g->Ci, (uint64_t)g->Co};
+    const uint64_t bs[1] = {(uint64_t)taps * g->Ci * 2};
+    const uint32_t bb[2] = {64, (uint32_t)p.BN};
+    if (int rc = make_map(&L.maps.b_hi, wf_hi, 2, bd, bs, bb)) return rc;
+    if (int rc = make_map(&L.maps.b_lo, wf_lo, 2, bd, bs, bb)) return rc;
+    L.grid = dim3((unsigned)(p.tiles_w * p.tiles_h * p.tiles_t * p.tiles_n), (unsigned)((g->Co + p.BN - 1) / p.BN));
+    return launch_conv(L, y, 0, as_stream(stream));
+}
+
+// dgrad, any stride in {1,2}: dx [NB,Ti,Hi,Wi,Ci] (+)= conv^T(dy planes [NB,To,Ho,Wo,Co], wd planes [Ci][taps][Co]).
+// One launch per input-parity class; with accumulate == 0 classes without taps are NOT written
+// (only possible for 1x1 strided sites, which the caller accumulates into an existing dx).
+extern "C" int dpc_conv3d_dgrad_tc(const dpc_conv_geom* g, const void* dy_hi, const void* dy_lo, const void* wd_hi,
+                                   const void* wd_lo, float* dx, int accumulate, void* stream) {
+    if (int rc = check_geom(g, "dpc_conv3d_dgrad_tc")) return rc;
+    DPC_REQUIRE(dy_hi && dy_lo && wd_hi && wd_lo && dx, "dpc_conv3d_dgrad_tc: null pointer");
+    const int taps = g->kT * g->kH * g->kW;
+    const long long rsw = 1, rsh = g->Wi, rst = (long long)g->Hi * g->Wi, rsn = (long long)g->Ti * g->Hi * g->Wi;
+    for (int ct = 0; ct < g->sT; ++ct)
+        for (int chh = 0; chh < g->sH; ++chh)
+            for (int cw = 0; cw < g->sW; ++cw) {
+                TcLaunch L;
+                memset(&L.p, 0, sizeof(L.p));
+                TcParams& p = L.p;
+                dgrad_taps(p.tT, g->kT, g->sT, g->pT, ct);
+                dgrad_taps(p.tH, g->kH, g->sH, g->pH, chh);
+                dgrad_taps(p.tW, g->kW, g->sW, g->pW, cw);
+                const int Tc = (g->Ti - ct + g->sT - 1) / g->sT, Hc = (g->Hi - chh + g->sH - 1) / g->sH,
+                          Wc = (g->Wi - cw + g->sW - 1) / g->sW;
+                if (Tc <= 0 || Hc <= 0 || Wc <= 0) continue;
+                if (p.tT.count == 0 || p.tH.count == 0 || p.tW.count == 0) {
+                    DPC_REQUIRE(accumulate, "dpc_conv3d_dgrad_tc: parity class without taps needs accumulate != 0");
+                    continue;
+                }
+                p.kH = g->kH; p.kW = g->kW; p.sH = 1; p.sW = 1; p.nviews = 1;
+                p.cchunks = g->Co / 64; p.Ksrc = g->Co;
+                set_tile_grid(p, g->NB, Tc, Hc, Wc, 128);
+                p.Co = g->Ci; p.BN = pick_bn(g->Ci);
+                set_stages(L, p.tT.count * p.tH.count * p.tW.count * p.cchunks);
+                p.out_sw = rsw * g->sW; p.out_sh = rsh * g->sH; p.out_st = rst * g->sT; p.out_sn = rsn;
+                p.out_base = ct * rst + chh * rsh + cw * rsw;
+                const uint32_t box[5] = {64, (uint32_t)p.bw, (uint32_t)p.bh, (uint32_t)p.bt, (uint32_t)p.bn};
+                const long long sw = g->Co, sh = (long long)g->Wo * sw, st = (long long)g->Ho * sh, sn = (long long)g->To * st;
+                if (int rc = make_act_map(&L.maps.a_hi[0], dy_hi, g->Co, g->Wo, g->Ho, g->To, g->NB, sw, sh, st, sn, box)) return rc;
+                if (int rc = make_act_map(&L.maps.a_lo[0], dy_lo, g->Co, g->Wo, g->Ho, g->To, g->NB, sw, sh, st, sn, box)) return rc;
+                const uint64_t bd[2] = {(uint64_t)taps * g->Co, (uint64_t)g->Ci};
+                const uint64_t bs[1] = {(uint64_t)taps * g->Co * 2};
+                const uint32_t bb[2] = {64, (uint32_t)p.BN};
+                if (int rc = make_map(&L.maps.b_hi, wd_hi, 2, bd, bs, bb)) return rc;
+                if (int rc = make_map(&L.maps.b_lo, wd_lo, 2, bd, bs, bb)) return rc;
+                L.grid = dim3((unsigned)(p.tiles_w * p.tiles_h * p.tiles_t * p.tiles_n), (unsigned)((g->Ci + p.BN - 1) / p.BN));
+                if (int rc = launch_conv(L, dx, accumulate, as_stream(stream))) return rc;
+            }
+    return DPC_OK;
+}
+
+// wgrad, any stride in {1,2}: dw [Co,Ci,kT,kH,kW] = sum_positions dy (x) x; `dwp` = scratch [Co][taps][Ci] fp32
+extern "C" int dpc_conv3d_wgrad_tc(const dpc_conv_geom* g, const void* x_hi, const void* x_lo, const void* dy_hi,
+                                   const void* dy_lo, float* dwp, float* dw, void* stream) {
+    if (int rc = check_geom(g, "dpc_conv3d_wgrad_tc")) return rc;
+    DPC_REQUIRE(x_hi && x_lo && dy_hi && dy_lo && dwp && dw, "dpc_conv3d_wgrad_tc: null pointer");
+    cudaStream_t st = as_stream(stream);
     const int taps = g->kT * g->kH * g->kW;
     TcLaunch L;
-    const long long sw = g->Ci, sh = (long long)g->Wi * sw, st = (long long)g->Hi * sh, sn = (long long)g->Ti * st;
-    if (int rc = setup(L, x_hi, x_lo, g->NB, g->Ti, g->Hi, g->Wi, g->Ci, sn, st, sh, sw, w_hi, w_lo, g->Co,
-                       taps * g->Ci, g->To, g->Ho, g->Wo, taps, g->kH, g->kW, -g->pT, -g->pH, -g->pW))
-        return rc;
-    return launch(L, y, accumulate, as_stream(stream));
+    memset(&L.p, 0, sizeof(L.p));
+    TcParams& p = L.p;
+    fwd_taps(p.tT, g->kT, g->sT, g->pT); fwd_taps(p.tH, g->kH, g->sH, g->pH); fwd_taps(p.tW, g->kW, g->sW, g->pW);
+    p.kH = g->kH; p.kW = g->kW; p.sH = g->sH; p.sW = g->sW; p.nviews = g->sT * g->sH * g->sW;
+    p.Ksrc = g->Ci; p.cchunks = g->Ci / 64;
+    set_tile_grid(p, g->NB, g->To, g->Ho, g->Wo, 64);           // K-block = up to 64 output positions
+    p.Co = g->Co; p.BN = pick_bn(g->Ci);
+    p.taps_full = taps;
+    const int total_tiles = p.tiles_w * p.tiles_h * p.tiles_t * p.tiles_n;
+    const int work = ((g->Co + 127) / 128) * ((g->Ci + p.BN - 1) / p.BN) * taps;
+    int splits = (2 * dpc_num_sms() + work - 1) / work;
+    if (splits < 1) splits = 1;
+    if (splits > total_tiles) splits = total_tiles;
+    p.ktiles_per_split = (total_tiles + splits - 1) / splits;
+    // bound the in-TMEM accumulation chain (truncating adds): <= 512 position tiles (2048 UMMA steps,
+    // ~ -4e-5 relative); longer reductions continue through the fp32 (round-to-nearest) atomics
+    if (p.ktiles_per_split > 512) p.ktiles_per_split = 512;
+    splits = (total_tiles + p.ktiles_per_split - 1) / p.ktiles_per_split;
+    DPC_REQUIRE(splits <= 65535, "dpc_conv3d_wgrad_tc: too many K splits (%d)", splits);
+    p.splits = splits;
+    set_stages(L, p.ktiles_per_split);
+    const uint32_t box[5] = {64, (uint32_t)p.bw, (uint32_t)p.bh, (uint32_t)p.bt, (uint32_t)p.bn};
+    if (int rc = make_parity_views(L.maps, g, x_hi, x_lo, box)) return rc;
+    const long long sw = g->Co, sh = (long long)g->Wo * sw, sT = (long long)g->Ho * sh, sn = (long long)g->To * sT;
+    if (int rc = make_act_map(&L.maps.b_hi, dy_hi, g->Co, g->Wo, g->Ho, g->To, g->NB, sw, sh, sT, sn, box)) return rc;
+    if (int rc = make_act_map(&L.maps.b_lo, dy_lo, g->Co, g->Wo, g->Ho, g->To, g->NB, sw, sh, sT, sn, box)) return rc;
+    DPC_CUDA(cudaMemsetAsync(dwp, 0, sizeof(float) * (size_t)g->Co * taps * g->Ci, st));
+    L.grid = dim3((unsigned)(((g->Co + 127) / 128) * ((g->Ci + p.BN - 1) / p.BN)), (unsigned)taps, (unsigned)splits);
+    DPC_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smem));
+    wgrad_tc_kernel<<<L.grid, 192, L.smem, st>>>(L.maps, L.p, dwp);
+    DPC_LAUNCH_CHECK();
+    long long total = (long long)g->Co * g->Ci * taps;
+    long long blocks = (total + 255) / 256;
+    long long cap = (long long)dpc_num_sms() * 8;
+    unpack_wgrad_ctc_kernel<<<(int)(blocks < cap ? blocks : cap), 256, 0, st>>>(dwp, dw, g->Co, g->Ci, taps);
+    DPC_LAUNCH_CHECK();
+    return DPC_OK;
 }

@@ -131,6 +131,59 @@ class ConvSite:
         return dw
 
 
+# tensor-core path switch: True = tcgen05 3xBF16-split kernels for every conv / the score matmul
+# (the default product path); False = exact-fp32 CUDA-core kernels (reference precision, used by
+# tests to cross-check the tensor-core path).
+USE_TC = True
+
+
+@_timed('split_bf16')
+def _split(x, st):
+    """fp32 rows -> (hi, lo) bf16 planes with hi + lo ~= x to ~2^-17"""
+    hi = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
+    lo = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
+    lib().split_bf16(ptr(x), ptr(hi), ptr(lo), x.numel(), st)
+    return hi, lo
+
+
+class TcConvSite(ConvSite):
+    """Conv3d call site on the tcgen05 kernels; activations/gradients are passed as (hi, lo) planes"""
+    __slots__ = ('wfh', 'wfl', 'wdh', 'wdl')
+
+    def pack(self, w, st):
+        bf = dict(dtype=torch.bfloat16, device=w.device)
+        self.wfh = torch.empty((self.Co, self.taps, self.Ci), **bf)
+        self.wfl = torch.empty((self.Co, self.taps, self.Ci), **bf)
+        self.wdh = torch.empty((self.Ci, self.taps, self.Co), **bf)
+        self.wdl = torch.empty((self.Ci, self.taps, self.Co), **bf)
+        lib().pack_conv_weight_bf16(ptr(w), ptr(self.wfh), ptr(self.wfl), ptr(self.wdh), ptr(self.wdl),
+                                    self.Co, self.Ci, self.taps, st)
+
+    @_timed('conv_fwd')
+    def fwd(self, xp, st):
+        y = torch.empty((self.rows_out, self.Co), dtype=torch.float32, device=xp[0].device)
+        lib().conv3d_fwd_tc(self.geom, ptr(xp[0]), ptr(xp[1]), ptr(self.wfh), ptr(self.wfl), ptr(y), st)
+        return y
+
+    @_timed('conv_dgrad')
+    def dgrad(self, dyp, st, dx=None):
+        acc = 1
+        if dx is None:
+            dx = torch.empty((self.rows_in, self.Ci), dtype=torch.float32, device=dyp[0].device)
+            acc = 0
+        lib().conv3d_dgrad_tc(self.geom, ptr(dyp[0]), ptr(dyp[1]), ptr(self.wdh), ptr(self.wdl), ptr(dx), acc, st)
+        return dx
+
+    @_timed('conv_wgrad')
+    def wgrad(self, xp, dyp, st):
+        g = self.geom
+        dev = xp[0].device
+        dwp = torch.empty((self.Co, self.taps, self.Ci), dtype=torch.float32, device=dev)
+        dw = torch.empty((self.Co, self.Ci, g.kT, g.kH, g.kW), dtype=torch.float32, device=dev)
+        lib().conv3d_wgrad_tc(g, ptr(xp[0]), ptr(xp[1]), ptr(dyp[0]), ptr(dyp[1]), ptr(dwp), ptr(dw), st)
+        return dw
+
+
 @_timed('bn_stats')
 def _bn_stats(y, rows, C, st):
     ws = torch.empty(2 * C, dtype=torch.float64, device=y.device)
@@ -194,7 +247,12 @@ def backbone_forward(network, x, P, need_ctx=True):
                           NB * T, Ho, Wo, 64, st)
     ctx = dict(network=network, x=x, y0=y0, m0=m0, r0=r0, a0=a0, stem_dims=(NB, T, H, W, Ho, Wo), blocks=[])
     cur, dims, C = a0, (T, Hp, Wp), 64
-    for b in backbone_spec(network):
+    tc = USE_TC
+    Site = TcConvSite if tc else ConvSite
+    opnd = (lambda t: _split(t, st)) if tc else (lambda t: t)      # conv operand: bf16 planes or fp32 rows
+    cur_op = opnd(cur)
+    spec = backbone_spec(network)
+    for bi, b in enumerate(spec):
         p = b['name']
         if b['is3d']:
             k, pad = (3, 3, 3), (1, 1, 1)
@@ -202,20 +260,22 @@ def backbone_forward(network, x, P, need_ctx=True):
         else:
             k, pad = (1, 3, 3), (0, 1, 1)
             s1 = (1, b['stride'], b['stride'])
-        c1 = ConvSite(NB, dims, b['inplanes'], b['planes'], k, s1, pad)
+        c1 = Site(NB, dims, b['inplanes'], b['planes'], k, s1, pad)
         c1.pack(P[p + '.conv1.weight'], st)
-        y1 = c1.fwd(cur, st)
+        y1 = c1.fwd(cur_op, st)
         m1, r1 = _bn_stats(y1, c1.rows_out, c1.Co, st)
         a1 = _bn_apply(y1, m1, r1, P[p + '.bn1.weight'], P[p + '.bn1.bias'], True, c1.rows_out, c1.Co, st)
-        c2 = ConvSite(NB, c1.dims_out, b['planes'], b['planes'], k, (1, 1, 1), pad)
+        a1_op = opnd(a1)
+        c2 = Site(NB, c1.dims_out, b['planes'], b['planes'], k, (1, 1, 1), pad)
         c2.pack(P[p + '.conv2.weight'], st)
-        y2 = c2.fwd(a1, st)
+        y2 = c2.fwd(a1_op, st)
         m2, r2 = _bn_stats(y2, c2.rows_out, c2.Co, st)
-        rec = dict(spec=b, c1=c1, c2=c2, xin=cur, y1=y1, m1=m1, r1=r1, a1=a1, y2=y2, m2=m2, r2=r2)
+        rec = dict(spec=b, c1=c1, c2=c2, xin=cur, xin_op=cur_op, y1=y1, m1=m1, r1=r1, a1=a1, a1_op=a1_op,
+                   y2=y2, m2=m2, r2=r2, tc=tc)
         if b['downsample']:
-            cd = ConvSite(NB, dims, b['inplanes'], b['planes'], (1, 1, 1), s1, (0, 0, 0))
+            cd = Site(NB, dims, b['inplanes'], b['planes'], (1, 1, 1), s1, (0, 0, 0))
             cd.pack(P[p + '.downsample.0.weight'], st)
-            yd = cd.fwd(cur, st)
+            yd = cd.fwd(cur_op, st)
             md, rd = _bn_stats(yd, cd.rows_out, cd.Co, st)
             out = _bn_apply(y2, m2, r2, P[p + '.bn2.weight'], P[p + '.bn2.bias'], b['final_relu'],
                             c2.rows_out, c2.Co, st, res=yd,
@@ -228,6 +288,8 @@ def backbone_forward(network, x, P, need_ctx=True):
         if need_ctx:
             ctx['blocks'].append(rec)
         cur, dims, C = out, c2.dims_out, b['planes']
+        if bi + 1 < len(spec):                       # the last block's output feeds the head, not a conv
+            cur_op = opnd(cur)
     return cur, dims, (ctx if need_ctx else None)
 
 
@@ -251,18 +313,22 @@ def backbone_backward(ctx, dout, P):
                 dout, rec['out'], relu, rec['yd'], rec['md'], rec['rd'], P[p + '.downsample.1.weight'],
                 cd.rows_out, cd.Co, st)
         del dout
-        G[p + '.conv2.weight'] = c2.wgrad(rec['a1'], dy2, st)
+        opnd = (lambda t: _split(t, st)) if rec['tc'] else (lambda t: t)
+        dy2 = opnd(dy2)
+        G[p + '.conv2.weight'] = c2.wgrad(rec['a1_op'], dy2, st)
         da1 = c2.dgrad(dy2, st)
         del dy2
         dy1, G[p + '.bn1.weight'], G[p + '.bn1.bias'], _ = _bn_bwd(
             da1, rec['a1'], True, rec['y1'], rec['m1'], rec['r1'], P[p + '.bn1.weight'],
             c1.rows_out, c1.Co, st)
         del da1
-        G[p + '.conv1.weight'] = c1.wgrad(rec['xin'], dy1, st)
+        dy1 = opnd(dy1)
+        G[p + '.conv1.weight'] = c1.wgrad(rec['xin_op'], dy1, st)
         if has_ds:
+            dyd = opnd(dyd)
             dx = c1.dgrad(dy1, st)
             cd.dgrad(dyd, st, dx=dx)
-            G[p + '.downsample.0.weight'] = cd.wgrad(rec['xin'], dyd, st)
+            G[p + '.downsample.0.weight'] = cd.wgrad(rec['xin_op'], dyd, st)
             del dyd
         else:
             dx = c1.dgrad(dy1, st, dx=g)          # dx = g + dgrad
@@ -420,7 +486,11 @@ def head_forward(z4, dims, B, N, pred_step, P, dropout_p=0.0, seed=0, need_ctx=T
     finf_rows = _empty((M, D), z4)
     L.gather_rows(ptr(finf_all), ptr(finf_rows), M, D, pred_step * S, N * S, Tagg * S, st)
     score = _empty((M, M), z4)
-    _gemm(0, 1, M, M, D, pred_rows, D, finf_rows, D, score, M, st)
+    if USE_TC:
+        pp, fp = _split(pred_rows, st), _split(finf_rows, st)
+        _timed('score_fwd')(L.gemm_nt_bf16x3_tc)(M, M, D, ptr(pp[0]), ptr(pp[1]), ptr(fp[0]), ptr(fp[1]), ptr(score), 0, st)
+    else:
+        _gemm(0, 1, M, M, D, pred_rows, D, finf_rows, D, score, M, st)
     ctx = None
     if need_ctx:
         ctx = dict(B=B, N=N, P=pred_step, S=S, D=D, To=To, R=R, M=M, finf_all=finf_all, X_all=X_all,
@@ -444,8 +514,22 @@ def head_backward(ctx, dscore, P):
     W0, W2 = P['network_pred.0.weight'], P['network_pred.2.weight']
     dpred_rows = _empty((M, D), dscore)
     dfinf_rows = _empty((M, D), dscore)
-    _gemm(0, 0, M, D, M, dscore, M, ctx['finf_rows'], D, dpred_rows, D, st)
-    _gemm(1, 0, M, D, M, dscore, M, ctx['pred_rows'], D, dfinf_rows, D, st)
+    if USE_TC and M % 64 == 0:
+        dsp = _split(dscore, st)
+        # dpred = dS . finf      -> NT GEMM against finf^T (tiny transpose: data movement only)
+        ftp = _split(ctx['finf_rows'].t().contiguous(), st)
+        _timed('score_bwd')(L.gemm_nt_bf16x3_tc)(M, D, M, ptr(dsp[0]), ptr(dsp[1]), ptr(ftp[0]), ptr(ftp[1]),
+                                                 ptr(dpred_rows), 0, st)
+        # dfinf = dS^T . pred    -> the wgrad form (reduction over rows, both operands MN-major)
+        pp = _split(ctx['pred_rows'], st)
+        geom = ConvGeom(1, 1, 1, M, D, 1, 1, M, M, 1, 1, 1, 1, 1, 1, 0, 0, 0)
+        scratch = _empty((M, D), dscore)
+        _timed('score_bwd')(L.conv3d_wgrad_tc)(geom, ptr(pp[0]), ptr(pp[1]), ptr(dsp[0]), ptr(dsp[1]), ptr(scratch),
+                                               ptr(dfinf_rows), st)
+        del dsp
+    else:
+        _gemm(0, 0, M, D, M, dscore, M, ctx['finf_rows'], D, dpred_rows, D, st)
+        _gemm(1, 0, M, D, M, dscore, M, ctx['pred_rows'], D, dfinf_rows, D, st)
     dfinf_all = torch.zeros((NB * S, D), dtype=torch.float32, device=dev)
     L.scatter_rows(ptr(dfinf_rows), ptr(dfinf_all), M, D, Pn * S, N * S, Tagg * S, 0, st)
     dfeat = torch.zeros((NB * S, D), dtype=torch.float32, device=dev)

@@ -59,17 +59,23 @@ int dpc_conv3d_wgrad(const dpc_conv_geom* g, const float* x, const float* dy, fl
  * (conv3x3x3 / conv1x3x3 / 1x1x1 at resnet_2d3d.py:13-31,241-244) plus torch.matmul at
  * dpc/model_3d.py:83.  Channel counts must be multiples of 64. */
 int dpc_split_bf16(const float* src, void* hi, void* lo, int64_t n, void* stream);
-/* w [Co,Ci,taps] -> forward planes wf_* [Co][tap][Ci] and (stride-1) dgrad planes wd_* [Ci][tap flipped][Co];
+/* w [Co,Ci,taps] -> forward planes wf_* [Co][tap][Ci] and dgrad planes wd_* [Ci][tap][Co];
  * either pair may be NULL */
 int dpc_pack_conv_weight_bf16(const float* w, void* wf_hi, void* wf_lo, void* wd_hi, void* wd_lo,
                               int Co, int Ci, int taps, void* stream);
-/* C[M,N] = A[M,K] * B[N,K]^T, fp32 out, K % 64 == 0 */
+/* C[M,N] (+)= A[M,K] * B[N,K]^T, fp32 out, K % 64 == 0 */
 int dpc_gemm_nt_bf16x3_tc(int M, int N, int K, const void* a_hi, const void* a_lo, const void* b_hi,
-                          const void* b_lo, float* C, void* stream);
-/* stride-1 conv: y (+)= conv(x planes, w planes [Co][taps][Ci]).  dgrad of a stride-1 site is the same
- * call with dy planes, the wd_* planes and the geometry's Ci/Co swapped. */
-int dpc_conv3d_s1_tc(const dpc_conv_geom* g, const void* x_hi, const void* x_lo, const void* w_hi,
-                     const void* w_lo, float* y, int accumulate, void* stream);
+                          const void* b_lo, float* C, int accumulate, void* stream);
+/* forward, strides in {1,2}: y = conv(x planes [NB,Ti,Hi,Wi,Ci], wf planes [Co][taps][Ci]) */
+int dpc_conv3d_fwd_tc(const dpc_conv_geom* g, const void* x_hi, const void* x_lo, const void* wf_hi,
+                      const void* wf_lo, float* y, void* stream);
+/* dgrad: dx (+)= conv^T(dy planes [NB,To,Ho,Wo,Co], wd planes [Ci][taps][Co]); one launch per
+ * input-parity class of a strided site */
+int dpc_conv3d_dgrad_tc(const dpc_conv_geom* g, const void* dy_hi, const void* dy_lo, const void* wd_hi,
+                        const void* wd_lo, float* dx, int accumulate, void* stream);
+/* wgrad: dw [Co,Ci,kT,kH,kW] = sum over positions dy (x) x; dwp = scratch [Co][taps][Ci] fp32 */
+int dpc_conv3d_wgrad_tc(const dpc_conv_geom* g, const void* x_hi, const void* x_lo, const void* dy_hi,
+                        const void* dy_lo, float* dwp, float* dw, void* stream);
 
 /* ---- stem: Conv3d(3,64,(1,7,7),s(1,2,2),p(0,3,3)) reading the caller's NCDHW input ----------
  * replaces backbone/resnet_2d3d.py:211,260 (self.conv1).  x [NB,3,T,H,W] -> y [NB,T,H/2,W/2,64]. */

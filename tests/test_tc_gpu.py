@@ -27,7 +27,7 @@ def _st():
 
 
 def rel(a, b):
-    a, b = a.double(), b.double()
+    a, b = a.detach().double(), b.detach().double()
     return float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
 
 
@@ -66,54 +66,84 @@ def test_gemm_nt_bf16x3(M, N, K):
     ah, al = split(A)
     bh, bl = split(B)
     C = torch.full((M, N), float('nan'), device='cuda')
-    L.gemm_nt_bf16x3_tc(M, N, K, ah.data_ptr(), al.data_ptr(), bh.data_ptr(), bl.data_ptr(), C.data_ptr(), _st())
+    L.gemm_nt_bf16x3_tc(M, N, K, ah.data_ptr(), al.data_ptr(), bh.data_ptr(), bl.data_ptr(), C.data_ptr(), 0, _st())
     torch.cuda.synchronize()
     ref = A.double() @ B.double().t()
     assert not torch.isnan(C).any()
     assert rel(C, ref) < 5e-5
+    C2 = torch.ones(M, N, device='cuda')
+    L.gemm_nt_bf16x3_tc(M, N, K, ah.data_ptr(), al.data_ptr(), bh.data_ptr(), bl.data_ptr(), C2.data_ptr(), 1, _st())
+    assert rel(C2, ref + 1) < 5e-5
 
 
 CASES = [
-    # NB, T, H, W, Ci, Co, k, p
-    (2, 5, 32, 32, 64, 64, (1, 3, 3), (0, 1, 1)),
-    (3, 5, 16, 16, 128, 128, (1, 3, 3), (0, 1, 1)),
-    (4, 3, 8, 8, 256, 256, (3, 3, 3), (1, 1, 1)),
-    (8, 2, 4, 4, 256, 256, (3, 3, 3), (1, 1, 1)),
-    (5, 2, 7, 7, 256, 256, (3, 3, 3), (1, 1, 1)),
-    (3, 3, 14, 14, 256, 256, (3, 3, 3), (1, 1, 1)),
-    (2, 5, 28, 28, 128, 128, (1, 3, 3), (0, 1, 1)),
-    (3, 1, 8, 8, 64, 128, (1, 1, 1), (0, 0, 0)),
+    # NB, T, H, W, Ci, Co, k, s, p
+    (2, 5, 32, 32, 64, 64, (1, 3, 3), (1, 1, 1), (0, 1, 1)),
+    (3, 5, 16, 16, 128, 128, (1, 3, 3), (1, 1, 1), (0, 1, 1)),
+    (4, 3, 8, 8, 256, 256, (3, 3, 3), (1, 1, 1), (1, 1, 1)),
+    (8, 2, 4, 4, 256, 256, (3, 3, 3), (1, 1, 1), (1, 1, 1)),
+    (5, 2, 7, 7, 256, 256, (3, 3, 3), (1, 1, 1), (1, 1, 1)),
+    (3, 3, 14, 14, 256, 256, (3, 3, 3), (1, 1, 1), (1, 1, 1)),
+    (2, 5, 28, 28, 128, 128, (1, 3, 3), (1, 1, 1), (0, 1, 1)),
+    (3, 1, 8, 8, 64, 128, (1, 1, 1), (1, 1, 1), (0, 0, 0)),
+    # strided sites of the backbone
+    (2, 5, 32, 32, 64, 128, (1, 3, 3), (1, 2, 2), (0, 1, 1)),       # layer2.0.conv1
+    (2, 5, 32, 32, 64, 128, (1, 1, 1), (1, 2, 2), (0, 0, 0)),       # layer2.0.downsample
+    (3, 5, 16, 16, 128, 256, (3, 3, 3), (2, 2, 2), (1, 1, 1)),      # layer3.0.conv1
+    (3, 5, 16, 16, 128, 256, (1, 1, 1), (2, 2, 2), (0, 0, 0)),      # layer3.0.downsample
+    (4, 3, 8, 8, 256, 256, (3, 3, 3), (2, 2, 2), (1, 1, 1)),        # layer4.0.conv1
+    (3, 3, 7, 7, 256, 256, (3, 3, 3), (2, 2, 2), (1, 1, 1)),        # odd extents
+    (2, 5, 28, 28, 64, 128, (1, 3, 3), (1, 2, 2), (0, 1, 1)),
 ]
 
 
+def _ext(i, k, s, p):
+    return (i + 2 * p - k) // s + 1
+
+
 @pytest.mark.parametrize('case', CASES)
-def test_conv_s1_fwd_and_dgrad(case):
+def test_conv_fwd_dgrad_wgrad_tc(case):
     L = _lib()
-    NB, T, H, W, Ci, Co, k, p = case
+    NB, T, H, W, Ci, Co, k, s, p = case
     taps = k[0] * k[1] * k[2]
+    To, Ho, Wo = _ext(T, k[0], s[0], p[0]), _ext(H, k[1], s[1], p[1]), _ext(W, k[2], s[2], p[2])
     g = torch.Generator(device='cuda').manual_seed(3)
     x = torch.randn(NB, Ci, T, H, W, device='cuda', generator=g)
     w = torch.randn(Co, Ci, *k, device='cuda', generator=g) / math.sqrt(Ci * taps)
     wfh = torch.empty(Co, taps, Ci, dtype=torch.bfloat16, device='cuda')
-    wfl, wdh, wdl = torch.empty_like(wfh), torch.empty(Ci, taps, Co, dtype=torch.bfloat16, device='cuda'), None
+    wfl = torch.empty_like(wfh)
+    wdh = torch.empty(Ci, taps, Co, dtype=torch.bfloat16, device='cuda')
     wdl = torch.empty_like(wdh)
     L.pack_conv_weight_bf16(w.data_ptr(), wfh.data_ptr(), wfl.data_ptr(), wdh.data_ptr(), wdl.data_ptr(), Co, Ci, taps, _st())
     xh, xl = split(to_rows(x))
-    geom = ConvGeom(NB, T, H, W, Ci, T, H, W, Co, k[0], k[1], k[2], 1, 1, 1, p[0], p[1], p[2])
-    y = torch.full((NB * T * H * W, Co), float('nan'), device='cuda')
-    L.conv3d_s1_tc(geom, xh.data_ptr(), xl.data_ptr(), wfh.data_ptr(), wfl.data_ptr(), y.data_ptr(), 0, _st())
+    geom = ConvGeom(NB, T, H, W, Ci, To, Ho, Wo, Co, k[0], k[1], k[2], s[0], s[1], s[2], p[0], p[1], p[2])
+    y = torch.full((NB * To * Ho * Wo, Co), float('nan'), device='cuda')
+    L.conv3d_fwd_tc(geom, xh.data_ptr(), xl.data_ptr(), wfh.data_ptr(), wfl.data_ptr(), y.data_ptr(), _st())
     torch.cuda.synchronize()
     xr = x.clone().requires_grad_(True)
-    yref = F.conv3d(xr, w, None, 1, p)
+    wr = w.clone().requires_grad_(True)
+    yref = F.conv3d(xr, wr, None, s, p)
+    assert tuple(yref.shape[2:]) == (To, Ho, Wo)
     assert not torch.isnan(y).any()
-    assert rel(from_rows(y, NB, T, H, W), yref) < 5e-5
-    # dgrad: same kernel on dy planes with the flipped/transposed weights
+    assert rel(from_rows(y, NB, To, Ho, Wo), yref) < 5e-5
     dy = torch.randn(yref.shape, device='cuda', generator=g)
     yref.backward(dy)
     dh, dl = split(to_rows(dy))
-    geom_d = ConvGeom(NB, T, H, W, Co, T, H, W, Ci, k[0], k[1], k[2], 1, 1, 1, p[0], p[1], p[2])
+    # dgrad (accumulating into a non-zero base: the 1x1 strided sites leave the other parity classes untouched)
     base = torch.randn(NB * T * H * W, Ci, device='cuda', generator=g)
     dx = base.clone()
-    L.conv3d_s1_tc(geom_d, dh.data_ptr(), dl.data_ptr(), wdh.data_ptr(), wdl.data_ptr(), dx.data_ptr(), 1, _st())
+    L.conv3d_dgrad_tc(geom, dh.data_ptr(), dl.data_ptr(), wdh.data_ptr(), wdl.data_ptr(), dx.data_ptr(), 1, _st())
     torch.cuda.synchronize()
     assert rel(dx - base, to_rows(xr.grad)) < 5e-5
+    if taps > 1 or s == (1, 1, 1):
+        dx0 = torch.full_like(base, float('nan'))
+        L.conv3d_dgrad_tc(geom, dh.data_ptr(), dl.data_ptr(), wdh.data_ptr(), wdl.data_ptr(), dx0.data_ptr(), 0, _st())
+        assert not torch.isnan(dx0).any()
+        assert rel(dx0, to_rows(xr.grad)) < 5e-5
+    # wgrad
+    dwp = torch.empty(Co, taps, Ci, device='cuda')
+    dw = torch.full_like(w, float('nan'))
+    L.conv3d_wgrad_tc(geom, xh.data_ptr(), xl.data_ptr(), dh.data_ptr(), dl.data_ptr(), dwp.data_ptr(), dw.data_ptr(), _st())
+    torch.cuda.synchronize()
+    assert not torch.isnan(dw).any()
+    assert rel(dw, wr.grad) < 5e-5

@@ -32,3 +32,16 @@ def check_sample(t, s, tol, what=''):
     assert err <= tol, '%s: sampled rel err %.3e > %.1e' % (what, err, tol)
     assert nerr <= tol, '%s: norm rel err %.3e > %.1e' % (what, nerr, tol)
     return err
+
+
+def check_sample_l2(t, s, tol, what=''):
+    """rel-L2 over the sampled entries (+ norm): the measure for chaotic quantities (tiny-batch gradients)"""
+    assert tuple(t.shape) == tuple(s['shape']), (what, t.shape, s['shape'])
+    f = t.detach().reshape(-1).float().cpu()
+    v = f[::s['step']][:s['values'].numel()].double()
+    ref = s['values'].double()
+    err = float((v - ref).norm() / ref.norm().clamp_min(1e-30))
+    nerr = abs(float(f.double().norm()) - s['norm']) / max(s['norm'], 1e-30)
+    assert err <= tol, '%s: sampled rel-L2 err %.3e > %.1e' % (what, err, tol)
+    assert nerr <= tol, '%s: norm rel err %.3e > %.1e' % (what, nerr, tol)
+    return err
