@@ -31,17 +31,21 @@ _SIGS = {
     'dpc_split_bf16': (c_int, [P, P, P, c_int64, P]),
     'dpc_pack_conv_weight_bf16': (c_int, [P, P, P, P, P, c_int, c_int, c_int, P]),
     'dpc_gemm_nt_bf16x3_tc': (c_int, [c_int, c_int, c_int, P, P, P, P, P, c_int, P]),
-    'dpc_conv3d_fwd_tc': (c_int, [POINTER(ConvGeom), P, P, P, P, P, P]),
+    'dpc_conv3d_fwd_tc': (c_int, [POINTER(ConvGeom), P, P, P, P, P, P, P]),
     'dpc_conv3d_dgrad_tc': (c_int, [POINTER(ConvGeom), P, P, P, P, P, c_int, P]),
     'dpc_conv3d_wgrad_tc': (c_int, [POINTER(ConvGeom), P, P, P, P, P, P, P]),
     'dpc_stem_conv_fwd': (c_int, [P, P, P, c_int, c_int, c_int, c_int, P]),
+    'dpc_stem_conv_fwd_tc': (c_int, [P, P, P, P, c_int, c_int, c_int, c_int, P]),
+    'dpc_stem_conv_wgrad_tc': (c_int, [P, P, P, P, c_int, c_int, c_int, c_int, P]),
     'dpc_stem_conv_wgrad': (c_int, [P, P, P, c_int, c_int, c_int, c_int, P]),
     'dpc_bn_stats': (c_int, [P, c_int64, c_int, P, P, P, c_float, P]),
-    'dpc_bn_apply_fwd': (c_int, [P, P, P, P, P, P, P, P, P, P, c_int, P, c_int64, c_int, P]),
-    'dpc_bn_bwd': (c_int, [P, P, c_int, P, P, P, P, P, P, P, P, P, c_int64, c_int, P]),
+    'dpc_bn_finalize': (c_int, [P, c_int64, c_int, c_float, P, P, P]),
+    'dpc_bn_apply_fwd': (c_int, [P, P, P, P, P, P, P, P, P, P, P, P, c_int, P, P, P, c_int64, c_int, P]),
+    'dpc_bn_bwd': (c_int, [P, P, P, c_int, P, P, P, P, P, P, P, P, P, P, P, c_int64, c_int, P]),
     'dpc_bn_relu_maxpool_fwd': (c_int, [P, P, P, P, P, P, c_int, c_int, c_int, c_int, P]),
     'dpc_bn_relu_maxpool_bwd': (c_int, [P, P, P, P, P, P, P, P, c_int, c_int, c_int, c_int, P]),
-    'dpc_pool_split_fwd': (c_int, [P, P, P, c_int, c_int, c_int, c_int, P]),
+    'dpc_stem_tail_bwd': (c_int, [P, P, P, P, P, P, P, P, P, P, P, P, P, c_int, c_int, c_int, c_int, P]),
+    'dpc_pool_split_fwd':(c_int, [P, P, P, c_int, c_int, c_int, c_int, P]),
     'dpc_pool_split_bwd': (c_int, [P, P, P, P, c_int, c_int, c_int, c_int, P]),
     'dpc_gemm_f32': (c_int, [c_int, c_int, c_int, c_int, c_int, c_float, P, c_int, P, c_int, c_float, P, c_int, P]),
     'dpc_gather_rows': (c_int, [P, P, c_int64, c_int, c_int64, c_int64, c_int64, P]),

@@ -80,14 +80,47 @@ __device__ __forceinline__ float4 affine(float4 v, const Affine4& a) {
                        fmaf(v.z - a.m.z, a.sc.z, a.b.z), fmaf(v.w - a.m.w, a.sc.w, a.b.w));
 }
 
-// RES: 0 none, 1 raw residual, 2 batch-normalised residual (downsample branch)
+// ---- split-bf16 planes (tensor-core operand format): value ~= hi + lo ----------------------------
+__device__ __forceinline__ float bf16_bits_to_float(uint32_t b) { return __uint_as_float(b << 16); }
+__device__ __forceinline__ float4 unpack_bf16x4(uint2 p) {
+    return make_float4(bf16_bits_to_float(p.x & 0xFFFFu), bf16_bits_to_float(p.x >> 16),
+                       bf16_bits_to_float(p.y & 0xFFFFu), bf16_bits_to_float(p.y >> 16));
+}
+__device__ __forceinline__ float4 ld4_hi(const void* hi, long long off) {
+    return unpack_bf16x4(*reinterpret_cast<const uint2*>(reinterpret_cast<const uint16_t*>(hi) + off));
+}
+__device__ __forceinline__ float4 ld4_planes(const void* hi, const void* lo, long long off) {
+    float4 a = ld4_hi(hi, off), b = ld4_hi(lo, off);
+    return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
+}
+__device__ __forceinline__ uint32_t f2bf_rn(float f) {      // round-to-nearest-even bf16 bits (finite inputs)
+    uint32_t u = __float_as_uint(f);
+    return (u + 0x7FFFu + ((u >> 16) & 1u)) >> 16;
+}
+__device__ __forceinline__ void st4_planes(void* hi, void* lo, long long off, float4 v) {
+    float f[4] = {v.x, v.y, v.z, v.w};
+    uint32_t h[4], l[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        h[j] = f2bf_rn(f[j]);
+        l[j] = f2bf_rn(f[j] - bf16_bits_to_float(h[j]));
+    }
+    *reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(hi) + off) = make_uint2(h[0] | (h[1] << 16), h[2] | (h[3] << 16));
+    *reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(lo) + off) = make_uint2(l[0] | (l[1] << 16), l[2] | (l[3] << 16));
+}
+
+// RES: 0 none, 1 raw residual (fp32 rows or bf16 planes), 2 batch-normalised residual (downsample branch)
+// Output: fp32 rows (`out`, nullable) and/or split-bf16 planes (`out_hi/out_lo`, nullable).
 template <int RES, bool RELU>
 __global__ void __launch_bounds__(THREADS) bn_apply_kernel(const float* __restrict__ y, const float* mean,
                                                             const float* rstd, const float* gamma,
                                                             const float* beta, const float* __restrict__ res,
+                                                            const void* __restrict__ res_hi,
+                                                            const void* __restrict__ res_lo,
                                                             const float* r_mean, const float* r_rstd,
                                                             const float* r_gamma, const float* r_beta,
-                                                            float* __restrict__ out, long long rows, int C) {
+                                                            float* __restrict__ out, void* __restrict__ out_hi,
+                                                            void* __restrict__ out_lo, long long rows, int C) {
     const int C4 = C / 4, rg = THREADS / C4;
     const int cq = threadIdx.x % C4, rl = threadIdx.x / C4;
     const Affine4 a = make_affine(mean, rstd, gamma, beta, cq * 4);
@@ -97,22 +130,25 @@ __global__ void __launch_bounds__(THREADS) bn_apply_kernel(const float* __restri
         const long long off = r * C + cq * 4;
         float4 v = affine(ld4(y + off), a);
         if (RES == 1) {
-            float4 q = ld4(res + off);
+            float4 q = res ? ld4(res + off) : ld4_planes(res_hi, res_lo, off);
             v.x += q.x; v.y += q.y; v.z += q.z; v.w += q.w;
         } else if (RES == 2) {
             float4 q = affine(ld4(res + off), ar);
             v.x += q.x; v.y += q.y; v.z += q.z; v.w += q.w;
         }
         if (RELU) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
-        st4(out + off, v);
+        if (out) st4(out + off, v);
+        if (out_hi) st4_planes(out_hi, out_lo, off, v);
     }
 }
 
 // ---- backward -------------------------------------------------------------------------------
-__device__ __forceinline__ float4 masked_grad(const float* dout, const float* out, long long off, bool relu) {
+// ReLU mask from the forward output: fp32 rows (`out`) or the hi plane (sign(hi) == sign(value))
+__device__ __forceinline__ float4 masked_grad(const float* dout, const float* out, const void* out_hi,
+                                              long long off, bool relu) {
     float4 g = ld4(dout + off);
     if (relu) {
-        float4 o = ld4(out + off);
+        float4 o = out ? ld4(out + off) : ld4_hi(out_hi, off);
         g.x = o.x > 0.f ? g.x : 0.f; g.y = o.y > 0.f ? g.y : 0.f;
         g.z = o.z > 0.f ? g.z : 0.f; g.w = o.w > 0.f ? g.w : 0.f;
     }
@@ -120,7 +156,8 @@ __device__ __forceinline__ float4 masked_grad(const float* dout, const float* ou
 }
 
 __global__ void __launch_bounds__(THREADS) bn_bwd_reduce_kernel(const float* __restrict__ dout,
-                                                                 const float* __restrict__ out, int relu,
+                                                                 const float* __restrict__ out,
+                                                                 const void* __restrict__ out_hi, int relu,
                                                                  const float* __restrict__ y, const float* mean,
                                                                  const float* rstd, long long rows, int C,
                                                                  double* __restrict__ ws) {
@@ -134,7 +171,7 @@ __global__ void __launch_bounds__(THREADS) bn_bwd_reduce_kernel(const float* __r
         long long end = base + chunk < rows ? base + chunk : rows;
         for (long long r = base + rl; r < end; r += rg) {
             const long long off = r * C + cq * 4;
-            float4 g = masked_grad(dout, out, off, relu != 0);
+            float4 g = masked_grad(dout, out, out_hi, off, relu != 0);
             float4 v = ld4(y + off);
             a.x += g.x; a.y += g.y; a.z += g.z; a.w += g.w;
             b.x = fmaf(g.x, (v.x - m.x) * rs.x, b.x); b.y = fmaf(g.y, (v.y - m.y) * rs.y, b.y);
@@ -155,11 +192,13 @@ __global__ void bn_bwd_finalize_kernel(const double* __restrict__ ws, int C, flo
 }
 
 __global__ void __launch_bounds__(THREADS) bn_bwd_apply_kernel(const float* __restrict__ dout,
-                                                                const float* __restrict__ out, int relu,
+                                                                const float* __restrict__ out,
+                                                                const void* __restrict__ out_hi, int relu,
                                                                 const float* __restrict__ y, const float* mean,
                                                                 const float* rstd, const float* gamma,
                                                                 const double* __restrict__ ws,
-                                                                float* __restrict__ dy, float* __restrict__ g_out,
+                                                                float* __restrict__ dy, void* __restrict__ dy_hi,
+                                                                void* __restrict__ dy_lo, float* __restrict__ g_out,
                                                                 long long rows, int C) {
     const int C4 = C / 4, rg = THREADS / C4;
     const int cq = threadIdx.x % C4, rl = threadIdx.x / C4;
@@ -172,14 +211,15 @@ __global__ void __launch_bounds__(THREADS) bn_bwd_apply_kernel(const float* __re
     const float k0 = ga.x * rs.x, k1 = ga.y * rs.y, k2 = ga.z * rs.z, k3 = ga.w * rs.w;
     for (long long r = (long long)blockIdx.x * rg + rl; r < rows; r += (long long)gridDim.x * rg) {
         const long long off = r * C + c;
-        float4 g = masked_grad(dout, out, off, relu != 0);
+        float4 g = masked_grad(dout, out, out_hi, off, relu != 0);
         float4 v = ld4(y + off);
         float4 d;
         d.x = k0 * (g.x - mb[0] - (v.x - m.x) * rs.x * mg[0]);
         d.y = k1 * (g.y - mb[1] - (v.y - m.y) * rs.y * mg[1]);
         d.z = k2 * (g.z - mb[2] - (v.z - m.z) * rs.z * mg[2]);
         d.w = k3 * (g.w - mb[3] - (v.w - m.w) * rs.w * mg[3]);
-        st4(dy + off, d);
+        if (dy) st4(dy + off, d);
+        if (dy_hi) st4_planes(dy_hi, dy_lo, off, d);
         if (g_out) st4(g_out + off, g);
     }
 }
@@ -253,6 +293,89 @@ __global__ void __launch_bounds__(THREADS) bn_relu_maxpool_bwd_kernel(const floa
     }
 }
 
+// ---- fused stem-tail backward: max-pool bwd + ReLU bwd + BN bwd without materialising g ----------
+// g(row, c) is recomputed on the fly in both BN-backward passes (see bn_relu_maxpool_bwd_kernel).
+__device__ __forceinline__ float4 stem_pool_grad(float4 v /* relu(bn(y)) pre-activation value */,
+                                                 const float* __restrict__ out, const float* __restrict__ dout,
+                                                 long long nt, int h, int w, int Ho, int Wo, int C, int cq) {
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int ho_lo = h >> 1, ho_hi = (h & 1) ? ho_lo + 1 : ho_lo;
+    const int wo_lo = w >> 1, wo_hi = (w & 1) ? wo_lo + 1 : wo_lo;
+    for (int ho = ho_lo; ho <= ho_hi; ++ho) {
+        if (ho >= Ho) continue;
+        for (int wo = wo_lo; wo <= wo_hi; ++wo) {
+            if (wo >= Wo) continue;
+            const long long o = ((nt * Ho + ho) * Wo + wo) * C + cq * 4;
+            const float4 p = ld4(out + o), d = ld4(dout + o);
+            if (v.x > 0.f && v.x == p.x) acc.x += d.x;
+            if (v.y > 0.f && v.y == p.y) acc.y += d.y;
+            if (v.z > 0.f && v.z == p.z) acc.z += d.z;
+            if (v.w > 0.f && v.w == p.w) acc.w += d.w;
+        }
+    }
+    return acc;
+}
+
+__global__ void __launch_bounds__(THREADS) stem_tail_bwd_reduce_kernel(
+    const float* __restrict__ y, const float* mean, const float* rstd, const float* gamma, const float* beta,
+    const float* __restrict__ out, const float* __restrict__ dout, int NT, int H, int W, int Ho, int Wo, int C,
+    double* __restrict__ ws) {
+    const int C4 = C / 4, rg = THREADS / C4;
+    const int cq = threadIdx.x % C4, rl = threadIdx.x / C4;
+    const Affine4 a = make_affine(mean, rstd, gamma, beta, cq * 4);
+    const float4 m = ld4(mean + cq * 4), rs = ld4(rstd + cq * 4);
+    const long long rows = (long long)NT * H * W;
+    double s[4] = {0, 0, 0, 0}, sx[4] = {0, 0, 0, 0};
+    const long long chunk = (long long)STRIP * rg;
+    for (long long base = (long long)blockIdx.x * chunk; base < rows; base += (long long)gridDim.x * chunk) {
+        float4 pa = make_float4(0.f, 0.f, 0.f, 0.f), pb = pa;
+        long long end = base + chunk < rows ? base + chunk : rows;
+        for (long long r = base + rl; r < end; r += rg) {
+            const int w = (int)(r % W), h = (int)((r / W) % H);
+            const long long nt = r / ((long long)W * H);
+            const float4 yv = ld4(y + r * C + cq * 4);
+            const float4 g = stem_pool_grad(affine(yv, a), out, dout, nt, h, w, Ho, Wo, C, cq);
+            pa.x += g.x; pa.y += g.y; pa.z += g.z; pa.w += g.w;
+            pb.x = fmaf(g.x, (yv.x - m.x) * rs.x, pb.x); pb.y = fmaf(g.y, (yv.y - m.y) * rs.y, pb.y);
+            pb.z = fmaf(g.z, (yv.z - m.z) * rs.z, pb.z); pb.w = fmaf(g.w, (yv.w - m.w) * rs.w, pb.w);
+        }
+        s[0] += pa.x; s[1] += pa.y; s[2] += pa.z; s[3] += pa.w;
+        sx[0] += pb.x; sx[1] += pb.y; sx[2] += pb.z; sx[3] += pb.w;
+    }
+    block_reduce_atomic(s, sx, cq, rl, C4, rg, ws, C);
+}
+
+__global__ void __launch_bounds__(THREADS) stem_tail_bwd_apply_kernel(
+    const float* __restrict__ y, const float* mean, const float* rstd, const float* gamma, const float* beta,
+    const float* __restrict__ out, const float* __restrict__ dout, int NT, int H, int W, int Ho, int Wo, int C,
+    const double* __restrict__ ws, float* __restrict__ dy, void* __restrict__ dy_hi, void* __restrict__ dy_lo) {
+    const int C4 = C / 4, rg = THREADS / C4;
+    const int cq = threadIdx.x % C4, rl = threadIdx.x / C4;
+    const int c = cq * 4;
+    const Affine4 a = make_affine(mean, rstd, gamma, beta, c);
+    const float4 m = ld4(mean + c), rs = ld4(rstd + c), ga = ld4(gamma + c);
+    const long long rows = (long long)NT * H * W;
+    const double inv_n = 1.0 / (double)rows;
+    float mb[4], mg[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { mb[i] = (float)(ws[c + i] * inv_n); mg[i] = (float)(ws[C + c + i] * inv_n); }
+    const float k0 = ga.x * rs.x, k1 = ga.y * rs.y, k2 = ga.z * rs.z, k3 = ga.w * rs.w;
+    for (long long r = (long long)blockIdx.x * rg + rl; r < rows; r += (long long)gridDim.x * rg) {
+        const int w = (int)(r % W), h = (int)((r / W) % H);
+        const long long nt = r / ((long long)W * H);
+        const long long off = r * C + c;
+        const float4 yv = ld4(y + off);
+        const float4 g = stem_pool_grad(affine(yv, a), out, dout, nt, h, w, Ho, Wo, C, cq);
+        float4 d;
+        d.x = k0 * (g.x - mb[0] - (yv.x - m.x) * rs.x * mg[0]);
+        d.y = k1 * (g.y - mb[1] - (yv.y - m.y) * rs.y * mg[1]);
+        d.z = k2 * (g.z - mb[2] - (yv.z - m.z) * rs.z * mg[2]);
+        d.w = k3 * (g.w - mb[3] - (yv.w - m.w) * rs.w * mg[3]);
+        if (dy) st4(dy + off, d);
+        if (dy_hi) st4_planes(dy_hi, dy_lo, off, d);
+    }
+}
+
 // ---- temporal average + ReLU split ------------------------------------------------------------
 __global__ void pool_split_fwd_kernel(const float* __restrict__ z, float* __restrict__ finf,
                                       float* __restrict__ feat, long long NB, int T, long long SC4) {
@@ -322,18 +445,31 @@ extern "C" int dpc_bn_stats(const float* y, int64_t rows, int C, double* ws, flo
     return DPC_OK;
 }
 
+// mean / rstd from sums accumulated elsewhere (the conv epilogue): ws = [sum[C] | sumsq[C]] doubles
+extern "C" int dpc_bn_finalize(const double* ws, int64_t rows, int C, float eps, float* mean, float* rstd, void* stream) {
+    DPC_REQUIRE(ws && mean && rstd && rows > 0 && C > 0, "dpc_bn_finalize: bad args");
+    bn_finalize_kernel<<<ceil_div(C, 128), 128, 0, as_stream(stream)>>>(ws, rows, C, eps, mean, rstd);
+    DPC_LAUNCH_CHECK();
+    return DPC_OK;
+}
+
 extern "C" int dpc_bn_apply_fwd(const float* y, const float* mean, const float* rstd, const float* gamma,
-                                const float* beta, const float* res, const float* r_mean, const float* r_rstd,
-                                const float* r_gamma, const float* r_beta, int relu, float* out,
+                                const float* beta, const float* res, const void* res_hi, const void* res_lo,
+                                const float* r_mean, const float* r_rstd, const float* r_gamma,
+                                const float* r_beta, int relu, float* out, void* out_hi, void* out_lo,
                                 int64_t rows, int C, void* stream) {
-    DPC_REQUIRE(y && mean && rstd && gamma && beta && out && rows > 0, "dpc_bn_apply_fwd: bad args");
+    DPC_REQUIRE(y && mean && rstd && gamma && beta && rows > 0, "dpc_bn_apply_fwd: bad args");
+    DPC_REQUIRE(out || (out_hi && out_lo), "dpc_bn_apply_fwd: no output");
+    DPC_REQUIRE(!out_hi == !out_lo && !res_hi == !res_lo, "dpc_bn_apply_fwd: planes come in pairs");
+    DPC_REQUIRE(!(res && res_hi), "dpc_bn_apply_fwd: residual given twice");
     if (int rc = check_c(C, "dpc_bn_apply_fwd")) return rc;
-    const int mode = res ? (r_mean ? 2 : 1) : 0;
+    const int mode = (res || res_hi) ? (r_mean ? 2 : 1) : 0;
+    if (mode == 2) DPC_REQUIRE(res, "dpc_bn_apply_fwd: the batch-normalised residual must be fp32 rows");
     if (mode == 2) DPC_REQUIRE(r_rstd && r_gamma && r_beta, "dpc_bn_apply_fwd: incomplete residual BN");
     cudaStream_t st = as_stream(stream);
     const int rg = THREADS / (C / 4);
     const int grid = stream_grid(rows, rg);
-#define LAUNCH(R, L) bn_apply_kernel<R, L><<<grid, THREADS, 0, st>>>(y, mean, rstd, gamma, beta, res, r_mean, r_rstd, r_gamma, r_beta, out, rows, C)
+#define LAUNCH(R, L) bn_apply_kernel<R, L><<<grid, THREADS, 0, st>>>(y, mean, rstd, gamma, beta, res, res_hi, res_lo, r_mean, r_rstd, r_gamma, r_beta, out, out_hi, out_lo, rows, C)
     if (mode == 0) { if (relu) LAUNCH(0, true); else LAUNCH(0, false); }
     else if (mode == 1) { if (relu) LAUNCH(1, true); else LAUNCH(1, false); }
     else { if (relu) LAUNCH(2, true); else LAUNCH(2, false); }
@@ -342,11 +478,14 @@ extern "C" int dpc_bn_apply_fwd(const float* y, const float* mean, const float* 
     return DPC_OK;
 }
 
-extern "C" int dpc_bn_bwd(const float* dout, const float* out, int relu, const float* y, const float* mean,
-                          const float* rstd, const float* gamma, double* ws, float* dgamma, float* dbeta,
-                          float* dy, float* g_out, int64_t rows, int C, void* stream) {
-    DPC_REQUIRE(dout && y && mean && rstd && gamma && ws && dgamma && dbeta && dy && rows > 0, "dpc_bn_bwd: bad args");
-    DPC_REQUIRE(!relu || out, "dpc_bn_bwd: relu needs the forward output");
+extern "C" int dpc_bn_bwd(const float* dout, const float* out, const void* out_hi, int relu, const float* y,
+                          const float* mean, const float* rstd, const float* gamma, double* ws, float* dgamma,
+                          float* dbeta, float* dy, void* dy_hi, void* dy_lo, float* g_out, int64_t rows, int C,
+                          void* stream) {
+    DPC_REQUIRE(dout && y && mean && rstd && gamma && ws && dgamma && dbeta && rows > 0, "dpc_bn_bwd: bad args");
+    DPC_REQUIRE(dy || (dy_hi && dy_lo), "dpc_bn_bwd: no output");
+    DPC_REQUIRE(!dy_hi == !dy_lo, "dpc_bn_bwd: planes come in pairs");
+    DPC_REQUIRE(!relu || out || out_hi, "dpc_bn_bwd: relu needs the forward output (rows or hi plane)");
     if (int rc = check_c(C, "dpc_bn_bwd")) return rc;
     cudaStream_t st = as_stream(stream);
     const int C4 = C / 4, rg = THREADS / C4;
@@ -354,12 +493,12 @@ extern "C" int dpc_bn_bwd(const float* dout, const float* out, int relu, const f
     long long chunks = (rows + (long long)STRIP * rg - 1) / ((long long)STRIP * rg);
     int grid = (int)(chunks < (long long)dpc_num_sms() * 8 ? chunks : (long long)dpc_num_sms() * 8);
     size_t smem = sizeof(double) * (size_t)rg * C4 * 8;
-    bn_bwd_reduce_kernel<<<grid, THREADS, smem, st>>>(dout, out, relu, y, mean, rstd, rows, C, ws);
+    bn_bwd_reduce_kernel<<<grid, THREADS, smem, st>>>(dout, out, out_hi, relu, y, mean, rstd, rows, C, ws);
     DPC_LAUNCH_CHECK();
     bn_bwd_finalize_kernel<<<ceil_div(C, 128), 128, 0, st>>>(ws, C, dgamma, dbeta);
     DPC_LAUNCH_CHECK();
-    bn_bwd_apply_kernel<<<stream_grid(rows, rg), THREADS, 0, st>>>(dout, out, relu, y, mean, rstd, gamma, ws, dy,
-                                                                   g_out, rows, C);
+    bn_bwd_apply_kernel<<<stream_grid(rows, rg), THREADS, 0, st>>>(dout, out, out_hi, relu, y, mean, rstd, gamma, ws,
+                                                                   dy, dy_hi, dy_lo, g_out, rows, C);
     DPC_LAUNCH_CHECK();
     return DPC_OK;
 }
@@ -385,6 +524,33 @@ extern "C" int dpc_bn_relu_maxpool_bwd(const float* y, const float* mean, const 
     const int rg = THREADS / (C / 4);
     bn_relu_maxpool_bwd_kernel<<<stream_grid((long long)NT * H * W, rg), THREADS, 0, as_stream(stream)>>>(
         y, mean, rstd, gamma, beta, out, dout, g, NT, H, W, Ho, Wo, C);
+    DPC_LAUNCH_CHECK();
+    return DPC_OK;
+}
+
+extern "C" int dpc_stem_tail_bwd(const float* y, const float* mean, const float* rstd, const float* gamma,
+                                 const float* beta, const float* out, const float* dout, double* ws, float* dgamma,
+                                 float* dbeta, float* dy, void* dy_hi, void* dy_lo, int NT, int H, int W, int C,
+                                 void* stream) {
+    DPC_REQUIRE(y && mean && rstd && gamma && beta && out && dout && ws && dgamma && dbeta && NT > 0,
+                "dpc_stem_tail_bwd: bad args");
+    DPC_REQUIRE(dy || (dy_hi && dy_lo), "dpc_stem_tail_bwd: no output");
+    DPC_REQUIRE(!dy_hi == !dy_lo, "dpc_stem_tail_bwd: planes come in pairs");
+    if (int rc = check_c(C, "dpc_stem_tail_bwd")) return rc;
+    cudaStream_t st = as_stream(stream);
+    const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
+    const int C4 = C / 4, rg = THREADS / C4;
+    const long long rows = (long long)NT * H * W;
+    DPC_CUDA(cudaMemsetAsync(ws, 0, sizeof(double) * 2 * C, st));
+    long long chunks = (rows + (long long)STRIP * rg - 1) / ((long long)STRIP * rg);
+    int grid = (int)(chunks < (long long)dpc_num_sms() * 8 ? chunks : (long long)dpc_num_sms() * 8);
+    size_t smem = sizeof(double) * (size_t)rg * C4 * 8;
+    stem_tail_bwd_reduce_kernel<<<grid, THREADS, smem, st>>>(y, mean, rstd, gamma, beta, out, dout, NT, H, W, Ho, Wo, C, ws);
+    DPC_LAUNCH_CHECK();
+    bn_bwd_finalize_kernel<<<ceil_div(C, 128), 128, 0, st>>>(ws, C, dgamma, dbeta);
+    DPC_LAUNCH_CHECK();
+    stem_tail_bwd_apply_kernel<<<stream_grid(rows, rg), THREADS, 0, st>>>(y, mean, rstd, gamma, beta, out, dout, NT, H, W,
+                                                                          Ho, Wo, C, ws, dy, dy_hi, dy_lo);
     DPC_LAUNCH_CHECK();
     return DPC_OK;
 }

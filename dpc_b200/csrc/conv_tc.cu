@@ -16,116 +16,9 @@
 //
 // Replaces nn.Conv3d fwd/bwd at backbone/resnet_2d3d.py:13-31,241-244 and torch.matmul at
 // dpc/model_3d.py:83.
-#include "common.cuh"
-#include <cudaTypedefs.h>
-#include <cuda_bf16.h>
+#include "tc_common.cuh"
 
 namespace {
-
-// ---------------------------------------------------------------------------------------------
-// PTX wrappers
-// ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-// Bounded wait: a protocol bug traps (-> CUDA error on the host) instead of hanging the GPU.
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    uint32_t done = 0;
-    const long long t0 = clock64();
-    for (;;) {
-        asm volatile(
-            "{\n\t"
-            ".reg .pred P1;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, P1;\n\t"
-            "}" : "=r"(done) : "r"(bar), "r"(parity) : "memory");
-        if (done) return;
-        if (clock64() - t0 > 4000000000ll) break;          // ~2 s: far beyond any legitimate wait
-    }
-    printf("dpc_b200: mbarrier wait timed out (block %d,%d,%d thread %d bar 0x%x parity %u)\n", blockIdx.x,
-           blockIdx.y, blockIdx.z, threadIdx.x, bar, parity);
-    __trap();
-}
-__device__ __forceinline__ void tma_load_5d(const CUtensorMap* map, uint32_t dst, uint32_t bar, int c0, int c1,
-                                            int c2, int c3, int c4) {
-    asm volatile(
-        "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
-        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4) : "memory");
-}
-__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint32_t dst, uint32_t bar, int c0, int c1) {
-    asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory");
-}
-__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
-}
-__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
-        "}" ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
-          "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
-          "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-        : "r"(taddr));
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ bool elect_one() {
-    uint32_t pred = 0;
-    asm volatile(
-        "{\n\t"
-        ".reg .pred P;\n\t"
-        "elect.sync _|P, 0xffffffff;\n\t"
-        "selp.u32 %0, 1, 0, P;\n\t"
-        "}" : "=r"(pred));
-    return pred != 0;
-}
-
-// K-major, 128B-swizzled operand tile: rows at 128-byte pitch, 8-row atoms 1024 bytes apart.
-__device__ __forceinline__ uint64_t make_kmajor_sw128_desc(uint32_t saddr) {
-    uint64_t d = 0;
-    d |= (uint64_t)((saddr >> 4) & 0x3FFF);        // start address
-    d |= (uint64_t)1 << 16;                        // leading byte offset (unused for swizzled K-major)
-    d |= (uint64_t)(1024 >> 4) << 32;              // stride byte offset: 8 rows * 128 B
-    d |= (uint64_t)1 << 46;                        // descriptor version (Blackwell)
-    d |= (uint64_t)2 << 61;                        // SWIZZLE_128B
-    return d;
-}
-// MN-major, 128B-swizzled: each smem row is one K index holding 64 contiguous MN elements (128 B);
-// 8 K-rows form a swizzle atom (SBO = 1024 B); 64-element MN groups are `lbo_bytes` apart.
-__device__ __forceinline__ uint64_t make_mnmajor_sw128_desc(uint32_t saddr, uint32_t lbo_bytes) {
-    uint64_t d = 0;
-    d |= (uint64_t)((saddr >> 4) & 0x3FFF);
-    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
-    d |= (uint64_t)(1024 >> 4) << 32;
-    d |= (uint64_t)1 << 46;
-    d |= (uint64_t)2 << 61;
-    return d;
-}
 
 // One filter-tap table entry per dimension: which original tap, which coordinate offset of the
 // gathered tensor relative to the tile origin, which parity view (strided convs).
@@ -201,10 +94,15 @@ __device__ __forceinline__ uint32_t setup_common(const SmemPlan& sp, const uint8
 // forward / dgrad / plain GEMM:  out[position, co] = sum_{tap, c} G[position (+) tap, c] * Wp[co][tap][c]
 // =============================================================================================
 __global__ void __launch_bounds__(192, 1)
-conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p, float* __restrict__ y, int accumulate) {
+conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p, float* __restrict__ y, int accumulate,
+               double* __restrict__ stats) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     const SmemPlan sp = plan_smem(smem_raw, p.BN, p.stages);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // per-CTA BatchNorm partials (sum | sum of squares), after the barrier block
+    float* stat_smem = reinterpret_cast<float*>(smem_raw + (sp.bar_base + 8u * (2 * p.stages + 2) - smem_u32(smem_raw)));
+    if (stats)
+        for (int i = threadIdx.x; i < 512; i += blockDim.x) stat_smem[i] = 0.f;
     // Two accumulators: columns [0,BN) take hi*hi, [BN,2BN) the two cross terms.  The TMEM accumulate
     // truncates (measured: mean relative error -2e-8 per accumulation step), so keeping the small terms
     // out of the main chain cuts that bias 3x; the epilogue adds the two in fp32 (round-to-nearest).
@@ -286,31 +184,64 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p, float* __r
             tmem_ld32(tmem_c + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, u);
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(u[j]));
-            if (!valid) continue;
-            if (vec && ncol0 + c0 + 32 <= p.Co) {
+            if (valid) {
+                if (vec && ncol0 + c0 + 32 <= p.Co) {
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    float4 o = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
-                                           __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
-                    float4* dst = reinterpret_cast<float4*>(yrow + c0) + j;
-                    if (accumulate) { float4 c = *dst; o.x += c.x; o.y += c.y; o.z += c.z; o.w += c.w; }
-                    *dst = o;
-                }
-            } else {
+                    for (int j = 0; j < 8; ++j) {
+                        float4 o = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
+                                               __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+                        float4* dst = reinterpret_cast<float4*>(yrow + c0) + j;
+                        if (accumulate) { float4 c = *dst; o.x += c.x; o.y += c.y; o.z += c.z; o.w += c.w; }
+                        *dst = o;
+                    }
+                } else {
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    if (ncol0 + c0 + j < p.Co) {
-                        float o = __uint_as_float(v[j]);
-                        if (accumulate) o += yrow[c0 + j];
-                        yrow[c0 + j] = o;
+                    for (int j = 0; j < 32; ++j) {
+                        if (ncol0 + c0 + j < p.Co) {
+                            float o = __uint_as_float(v[j]);
+                            if (accumulate) o += yrow[c0 + j];
+                            yrow[c0 + j] = o;
+                        }
                     }
                 }
+            }
+            if (stats) {
+                // BatchNorm statistics of this tile, fused into the producer: per-column sum / sum of
+                // squares over the warp's 32 rows by a 31-shuffle transposing butterfly (lane l ends up
+                // with column c0+l), then shared-memory partials per CTA.
+                float sv[32], sq[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const float f = valid ? __uint_as_float(v[j]) : 0.f;
+                    sv[j] = f; sq[j] = f * f;
+                }
+#pragma unroll
+                for (int off = 16; off >= 1; off >>= 1) {
+                    const bool up = (lane & off) != 0;
+#pragma unroll
+                    for (int i = 0; i < off; ++i) {
+                        const float s_send = up ? sv[i] : sv[i + off], s_keep = up ? sv[i + off] : sv[i];
+                        const float q_send = up ? sq[i] : sq[i + off], q_keep = up ? sq[i + off] : sq[i];
+                        sv[i] = s_keep + __shfl_xor_sync(0xffffffffu, s_send, off);
+                        sq[i] = q_keep + __shfl_xor_sync(0xffffffffu, q_send, off);
+                    }
+                }
+                atomicAdd(&stat_smem[c0 + lane], sv[0]);
+                atomicAdd(&stat_smem[256 + c0 + lane], sq[0]);
             }
         }
     }
     tc_fence_before();
     __syncthreads();
     if (warp == 1) tmem_dealloc(tmem_d, tmem_cols);
+    if (stats) {
+        for (int c = threadIdx.x; c < p.BN; c += blockDim.x) {
+            if (ncol0 + c < p.Co) {
+                atomicAdd(stats + ncol0 + c, (double)stat_smem[c]);
+                atomicAdd(stats + p.Co + ncol0 + c, (double)stat_smem[256 + c]);
+            }
+        }
+    }
 }
 
 // =============================================================================================
@@ -507,7 +438,7 @@ void set_stages(TcLaunch& L, int num_kb) {
     if (stages > num_kb) stages = num_kb;
     if (stages < 1) stages = 1;
     p.stages = stages;
-    L.smem = (size_t)stages * stage_bytes + 8 * (2 * stages + 2) + 1024;
+    L.smem = (size_t)stages * stage_bytes + 8 * (2 * stages + 2) + 2048 /* BN partials */ + 1024 /* alignment */;
 }
 
 int pick_bn(int C) { return C >= 256 ? 256 : (C >= 128 ? 128 : (C >= 64 ? 64 : 32)); }
@@ -568,9 +499,9 @@ int make_parity_views(TcMaps& maps, const dpc_conv_geom* g, const void* x_hi, co
     return DPC_OK;
 }
 
-int launch_conv(TcLaunch& L, float* y, int accumulate, cudaStream_t st) {
+int launch_conv(TcLaunch& L, float* y, int accumulate, cudaStream_t st, double* stats = nullptr) {
     DPC_CUDA(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smem));
-    conv_tc_kernel<<<L.grid, 192, L.smem, st>>>(L.maps, L.p, y, accumulate);
+    conv_tc_kernel<<<L.grid, 192, L.smem, st>>>(L.maps, L.p, y, accumulate, stats);
     DPC_LAUNCH_CHECK();
     return DPC_OK;
 }
@@ -689,7 +620,7 @@ extern "C" int dpc_gemm_nt_bf16x3_tc(int M, int N, int K, const void* a_hi, cons
 
 // forward conv, any stride in {1,2}: y [NB,To,Ho,Wo,Co] = conv(x planes [NB,Ti,Hi,Wi,Ci], wf planes [Co][taps][Ci])
 extern "C" int dpc_conv3d_fwd_tc(const dpc_conv_geom* g, const void* x_hi, const void* x_lo, const void* wf_hi,
-                                 const void* wf_lo, float* y, void* stream) {
+                                 const void* wf_lo, float* y, double* bn_ws, void* stream) {
     if (int rc = check_geom(g, "dpc_conv3d_fwd_tc")) return rc;
     DPC_REQUIRE(x_hi && x_lo && wf_hi && wf_lo && y, "dpc_conv3d_fwd_tc: null pointer");
     TcLaunch L;
@@ -712,7 +643,8 @@ extern "C" int dpc_conv3d_fwd_tc(const dpc_conv_geom* g, const void* x_hi, const
     if (int rc = make_map(&L.maps.b_hi, wf_hi, 2, bd, bs, bb)) return rc;
     if (int rc = make_map(&L.maps.b_lo, wf_lo, 2, bd, bs, bb)) return rc;
     L.grid = dim3((unsigned)(p.tiles_w * p.tiles_h * p.tiles_t * p.tiles_n), (unsigned)((g->Co + p.BN - 1) / p.BN));
-    return launch_conv(L, y, 0, as_stream(stream));
+    if (bn_ws) DPC_CUDA(cudaMemsetAsync(bn_ws, 0, sizeof(double) * 2 * g->Co, as_stream(stream)));
+    return launch_conv(L, y, 0, as_stream(stream), bn_ws);
 }
 
 // dgrad, any stride in {1,2}: dx [NB,Ti,Hi,Wi,Ci] (+)= conv^T(dy planes [NB,To,Ho,Wo,Co], wd planes [Ci][taps][Co]).

@@ -7,11 +7,12 @@ namespace {
 
 constexpr int TM = 64, TN = 64, TK = 16;
 
-template <bool TA, bool TB>
+// SPLITK: grid.z slices of K; partial products are added to C with fp32 atomics (C pre-scaled by beta)
+template <bool TA, bool TB, bool SPLITK>
 __global__ void __launch_bounds__(256) gemm_f32_kernel(int M, int N, int K, float alpha,
                                                         const float* __restrict__ A, int lda,
                                                         const float* __restrict__ B, int ldb,
-                                                        float beta, float* __restrict__ C, int ldc) {
+                                                        float beta, float* __restrict__ C, int ldc, int kslice) {
     __shared__ float As[TK][TM + 4];
     __shared__ float Bs[TK][TN + 4];
     const int tid = threadIdx.x;
@@ -23,7 +24,9 @@ __global__ void __launch_bounds__(256) gemm_f32_kernel(int M, int N, int K, floa
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
 
-    for (int k0 = 0; k0 < K; k0 += TK) {
+    const int kbeg = SPLITK ? blockIdx.z * kslice : 0;
+    const int kend = SPLITK ? (kbeg + kslice < K ? kbeg + kslice : K) : K;
+    for (int k0 = kbeg; k0 < kend; k0 += TK) {
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
             int idx = tid + e * 256;
@@ -31,7 +34,7 @@ __global__ void __launch_bounds__(256) gemm_f32_kernel(int M, int N, int K, floa
             if (TA) { k = idx / TM; m = idx % TM; } else { m = idx / TK; k = idx % TK; }
             int gm = m0 + m, gk = k0 + k;
             float v = 0.f;
-            if (gm < M && gk < K) v = TA ? A[(size_t)gk * lda + gm] : A[(size_t)gm * lda + gk];
+            if (gm < M && gk < kend) v = TA ? A[(size_t)gk * lda + gm] : A[(size_t)gm * lda + gk];
             As[k][m] = v;
         }
 #pragma unroll
@@ -41,7 +44,7 @@ __global__ void __launch_bounds__(256) gemm_f32_kernel(int M, int N, int K, floa
             if (TB) { n = idx / TK; k = idx % TK; } else { k = idx / TN; n = idx % TN; }
             int gn = n0 + n, gk = k0 + k;
             float v = 0.f;
-            if (gn < N && gk < K) v = TB ? B[(size_t)gn * ldb + gk] : B[(size_t)gk * ldb + gn];
+            if (gn < N && gk < kend) v = TB ? B[(size_t)gn * ldb + gk] : B[(size_t)gk * ldb + gn];
             Bs[k][n] = v;
         }
         __syncthreads();
@@ -67,9 +70,18 @@ __global__ void __launch_bounds__(256) gemm_f32_kernel(int M, int N, int K, floa
             if (gn >= N) continue;
             float* c = &C[(size_t)gm * ldc + gn];
             float v = alpha * acc[i][j];
+            if (SPLITK) { atomicAdd(c, v); continue; }
             if (beta != 0.f) v += beta * (*c);
             *c = v;
         }
+    }
+}
+
+__global__ void scale_matrix_kernel(float* __restrict__ C, int M, int N, int ldc, float beta) {
+    long long total = (long long)M * N;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        float* c = &C[(size_t)(i / N) * ldc + (i % N)];
+        *c = beta == 0.f ? 0.f : beta * (*c);
     }
 }
 
@@ -132,10 +144,38 @@ extern "C" int dpc_gemm_f32(int transA, int transB, int M, int N, int K, float a
     DPC_REQUIRE(A && B && C, "dpc_gemm_f32: null pointer");
     dim3 grid(ceil_div(N, TN), ceil_div(M, TM));
     cudaStream_t st = as_stream(stream);
-    if (!transA && !transB) gemm_f32_kernel<false, false><<<grid, 256, 0, st>>>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc);
-    else if (!transA && transB) gemm_f32_kernel<false, true><<<grid, 256, 0, st>>>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc);
-    else if (transA && !transB) gemm_f32_kernel<true, false><<<grid, 256, 0, st>>>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc);
-    else gemm_f32_kernel<true, true><<<grid, 256, 0, st>>>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc);
+    // few output tiles but a long reduction (the GRU / predictor weight gradients: 256x256 outputs over
+    // thousands of rows): slice K across CTAs so the whole chip works on it
+    const int tiles = (int)(grid.x * grid.y);
+    int splits = 1;
+    if (tiles < dpc_num_sms() && K >= 512) {
+        splits = (2 * dpc_num_sms() + tiles - 1) / tiles;
+        if (splits > K / 128) splits = K / 128;
+        if (splits < 1) splits = 1;
+    }
+    if (splits > 1) {
+        int kslice = ((K + splits - 1) / splits + TK - 1) / TK * TK;
+        splits = (K + kslice - 1) / kslice;
+        if (beta != 1.f) {
+            scale_matrix_kernel<<<ceil_div((long long)M * N, 256), 256, 0, st>>>(C, M, N, ldc, beta);
+            DPC_LAUNCH_CHECK();
+        }
+        grid.z = splits;
+#define GEMM_SK(TA_, TB_) gemm_f32_kernel<TA_, TB_, true><<<grid, 256, 0, st>>>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, kslice)
+        if (!transA && !transB) GEMM_SK(false, false);
+        else if (!transA && transB) GEMM_SK(false, true);
+        else if (transA && !transB) GEMM_SK(true, false);
+        else GEMM_SK(true, true);
+#undef GEMM_SK
+        DPC_LAUNCH_CHECK();
+        return DPC_OK;
+    }
+#define GEMM_1(TA_, TB_) gemm_f32_kernel<TA_, TB_, false><<<grid, 256, 0, st>>>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, K)
+    if (!transA && !transB) GEMM_1(false, false);
+    else if (!transA && transB) GEMM_1(false, true);
+    else if (transA && !transB) GEMM_1(true, false);
+    else GEMM_1(true, true);
+#undef GEMM_1
     DPC_LAUNCH_CHECK();
     return DPC_OK;
 }

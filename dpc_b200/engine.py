@@ -110,6 +110,12 @@ class ConvSite:
         lib().conv3d_fwd(self.geom, ptr(x), ptr(self.wf), ptr(y), st)
         return y
 
+    def fwd_bn(self, x, st):
+        """conv + BatchNorm batch statistics -> (y, mean, rstd)"""
+        y = self.fwd(x, st)
+        mean, rstd = _bn_stats(y, self.rows_out, self.Co, st)
+        return y, mean, rstd
+
     @_timed('conv_dgrad')
     def dgrad(self, dy, st, dx=None):
         acc = 1
@@ -162,8 +168,21 @@ class TcConvSite(ConvSite):
     @_timed('conv_fwd')
     def fwd(self, xp, st):
         y = torch.empty((self.rows_out, self.Co), dtype=torch.float32, device=xp[0].device)
-        lib().conv3d_fwd_tc(self.geom, ptr(xp[0]), ptr(xp[1]), ptr(self.wfh), ptr(self.wfl), ptr(y), st)
+        lib().conv3d_fwd_tc(self.geom, ptr(xp[0]), ptr(xp[1]), ptr(self.wfh), ptr(self.wfl), ptr(y), None, st)
         return y
+
+    @_timed('conv_fwd')
+    def fwd_bn(self, xp, st):
+        """conv + fused BatchNorm batch statistics -> (y, mean, rstd)"""
+        dev = xp[0].device
+        y = torch.empty((self.rows_out, self.Co), dtype=torch.float32, device=dev)
+        ws = torch.empty(2 * self.Co, dtype=torch.float64, device=dev)
+        mean = torch.empty(self.Co, dtype=torch.float32, device=dev)
+        rstd = torch.empty(self.Co, dtype=torch.float32, device=dev)
+        L = lib()
+        L.conv3d_fwd_tc(self.geom, ptr(xp[0]), ptr(xp[1]), ptr(self.wfh), ptr(self.wfl), ptr(y), ptr(ws), st)
+        L.bn_finalize(ptr(ws), self.rows_out, self.Co, BN_EPS, ptr(mean), ptr(rstd), st)
+        return y, mean, rstd
 
     @_timed('conv_dgrad')
     def dgrad(self, dyp, st, dx=None):
@@ -194,24 +213,39 @@ def _bn_stats(y, rows, C, st):
 
 
 @_timed('bn_apply')
-def _bn_apply(y, mean, rstd, gamma, beta, relu, rows, C, st, res=None, rbn=None):
-    out = torch.empty_like(y)
+def _bn_apply(y, mean, rstd, gamma, beta, relu, rows, C, st, res=None, res_planes=None, rbn=None,
+              want_rows=True, want_planes=False):
+    """[relu](bn(y) + residual) -> (fp32 rows or None, (hi, lo) planes or None)"""
+    out = torch.empty_like(y) if want_rows else None
+    planes = None
+    if want_planes:
+        planes = (torch.empty(y.shape, dtype=torch.bfloat16, device=y.device),
+                  torch.empty(y.shape, dtype=torch.bfloat16, device=y.device))
     r = rbn if rbn is not None else (None, None, None, None)
-    lib().bn_apply_fwd(ptr(y), ptr(mean), ptr(rstd), ptr(gamma), ptr(beta), ptr(res), ptr(r[0]), ptr(r[1]),
-                       ptr(r[2]), ptr(r[3]), 1 if relu else 0, ptr(out), rows, C, st)
-    return out
+    rp = res_planes if (res is None and res_planes is not None) else (None, None)
+    lib().bn_apply_fwd(ptr(y), ptr(mean), ptr(rstd), ptr(gamma), ptr(beta), ptr(res), ptr(rp[0]), ptr(rp[1]),
+                       ptr(r[0]), ptr(r[1]), ptr(r[2]), ptr(r[3]), 1 if relu else 0, ptr(out),
+                       ptr(planes[0]) if planes else None, ptr(planes[1]) if planes else None, rows, C, st)
+    return out, planes
 
 
 @_timed('bn_bwd')
-def _bn_bwd(dout, out, relu, y, mean, rstd, gamma, rows, C, st, want_g=False):
+def _bn_bwd(dout, out, relu, y, mean, rstd, gamma, rows, C, st, want_g=False, out_hi=None, want_rows=True,
+            want_planes=False):
+    """-> (dy rows or None, dy planes or None, dgamma, dbeta, g or None)"""
     ws = torch.empty(2 * C, dtype=torch.float64, device=y.device)
     dgamma = _empty((C,), y)
     dbeta = _empty((C,), y)
-    dy = torch.empty_like(y)
+    dy = torch.empty_like(y) if want_rows else None
+    planes = None
+    if want_planes:
+        planes = (torch.empty(y.shape, dtype=torch.bfloat16, device=y.device),
+                  torch.empty(y.shape, dtype=torch.bfloat16, device=y.device))
     g = torch.empty_like(y) if want_g else None
-    lib().bn_bwd(ptr(dout), ptr(out), 1 if relu else 0, ptr(y), ptr(mean), ptr(rstd), ptr(gamma), ptr(ws),
-                 ptr(dgamma), ptr(dbeta), ptr(dy), ptr(g), rows, C, st)
-    return dy, dgamma, dbeta, g
+    lib().bn_bwd(ptr(dout), ptr(out), ptr(out_hi) if out is None else None, 1 if relu else 0, ptr(y), ptr(mean),
+                 ptr(rstd), ptr(gamma), ptr(ws), ptr(dgamma), ptr(dbeta), ptr(dy),
+                 ptr(planes[0]) if planes else None, ptr(planes[1]) if planes else None, ptr(g), rows, C, st)
+    return dy, planes, dgamma, dbeta, g
 
 
 # ==================================================================================================
@@ -239,8 +273,14 @@ def backbone_forward(network, x, P, need_ctx=True):
     Ho, Wo = _out_extent(H, 7, 2, 3), _out_extent(W, 7, 2, 3)
     rows0 = NB * T * Ho * Wo
     y0 = _empty((rows0, 64), x)
-    _timed('stem_fwd')(L.stem_conv_fwd)(ptr(x), ptr(P['conv1.weight']), ptr(y0), NB, T, H, W, st)
-    m0, r0 = _bn_stats(y0, rows0, 64, st)
+    if USE_TC:
+        ws0 = torch.empty(128, dtype=torch.float64, device=x.device)
+        m0, r0 = _empty((64,), x), _empty((64,), x)
+        _timed('stem_fwd')(L.stem_conv_fwd_tc)(ptr(x), ptr(P['conv1.weight']), ptr(y0), ptr(ws0), NB, T, H, W, st)
+        L.bn_finalize(ptr(ws0), rows0, 64, BN_EPS, ptr(m0), ptr(r0), st)
+    else:
+        _timed('stem_fwd')(L.stem_conv_fwd)(ptr(x), ptr(P['conv1.weight']), ptr(y0), NB, T, H, W, st)
+        m0, r0 = _bn_stats(y0, rows0, 64, st)
     Hp, Wp = _out_extent(Ho, 3, 2, 1), _out_extent(Wo, 3, 2, 1)
     a0 = _empty((NB * T * Hp * Wp, 64), x)
     _timed('stem_pool_fwd')(L.bn_relu_maxpool_fwd)(ptr(y0), ptr(m0), ptr(r0), ptr(P['bn1.weight']), ptr(P['bn1.bias']), ptr(a0),
@@ -249,11 +289,12 @@ def backbone_forward(network, x, P, need_ctx=True):
     cur, dims, C = a0, (T, Hp, Wp), 64
     tc = USE_TC
     Site = TcConvSite if tc else ConvSite
-    opnd = (lambda t: _split(t, st)) if tc else (lambda t: t)      # conv operand: bf16 planes or fp32 rows
-    cur_op = opnd(cur)
+    # conv operands: split-bf16 planes on the tensor-core path, fp32 rows on the CUDA-core path
+    cur_op = _split(cur, st) if tc else cur
     spec = backbone_spec(network)
     for bi, b in enumerate(spec):
         p = b['name']
+        last = bi + 1 == len(spec)
         if b['is3d']:
             k, pad = (3, 3, 3), (1, 1, 1)
             s1 = (b['stride'],) * 3
@@ -262,34 +303,36 @@ def backbone_forward(network, x, P, need_ctx=True):
             s1 = (1, b['stride'], b['stride'])
         c1 = Site(NB, dims, b['inplanes'], b['planes'], k, s1, pad)
         c1.pack(P[p + '.conv1.weight'], st)
-        y1 = c1.fwd(cur_op, st)
-        m1, r1 = _bn_stats(y1, c1.rows_out, c1.Co, st)
-        a1 = _bn_apply(y1, m1, r1, P[p + '.bn1.weight'], P[p + '.bn1.bias'], True, c1.rows_out, c1.Co, st)
-        a1_op = opnd(a1)
+        y1, m1, r1 = c1.fwd_bn(cur_op, st)
+        # tensor-core path: the normalise pass writes the next conv's operand planes directly
+        a1, a1_pl = _bn_apply(y1, m1, r1, P[p + '.bn1.weight'], P[p + '.bn1.bias'], True, c1.rows_out, c1.Co, st,
+                              want_rows=not tc, want_planes=tc)
+        a1_op = a1_pl if tc else a1
         c2 = Site(NB, c1.dims_out, b['planes'], b['planes'], k, (1, 1, 1), pad)
         c2.pack(P[p + '.conv2.weight'], st)
-        y2 = c2.fwd(a1_op, st)
-        m2, r2 = _bn_stats(y2, c2.rows_out, c2.Co, st)
-        rec = dict(spec=b, c1=c1, c2=c2, xin=cur, xin_op=cur_op, y1=y1, m1=m1, r1=r1, a1=a1, a1_op=a1_op,
+        y2, m2, r2 = c2.fwd_bn(a1_op, st)
+        rec = dict(spec=b, c1=c1, c2=c2, xin_op=cur_op, y1=y1, m1=m1, r1=r1, a1=a1, a1_op=a1_op,
                    y2=y2, m2=m2, r2=r2, tc=tc)
+        want_rows = (not tc) or last                 # the last block's output feeds the head as fp32 rows
+        want_planes = tc and not last
         if b['downsample']:
             cd = Site(NB, dims, b['inplanes'], b['planes'], (1, 1, 1), s1, (0, 0, 0))
             cd.pack(P[p + '.downsample.0.weight'], st)
-            yd = cd.fwd(cur_op, st)
-            md, rd = _bn_stats(yd, cd.rows_out, cd.Co, st)
-            out = _bn_apply(y2, m2, r2, P[p + '.bn2.weight'], P[p + '.bn2.bias'], b['final_relu'],
-                            c2.rows_out, c2.Co, st, res=yd,
-                            rbn=(md, rd, P[p + '.downsample.1.weight'], P[p + '.downsample.1.bias']))
+            yd, md, rd = cd.fwd_bn(cur_op, st)
+            out, out_pl = _bn_apply(y2, m2, r2, P[p + '.bn2.weight'], P[p + '.bn2.bias'], b['final_relu'],
+                                    c2.rows_out, c2.Co, st, res=yd,
+                                    rbn=(md, rd, P[p + '.downsample.1.weight'], P[p + '.downsample.1.bias']),
+                                    want_rows=want_rows, want_planes=want_planes)
             rec.update(cd=cd, yd=yd, md=md, rd=rd)
         else:
-            out = _bn_apply(y2, m2, r2, P[p + '.bn2.weight'], P[p + '.bn2.bias'], b['final_relu'],
-                            c2.rows_out, c2.Co, st, res=cur)
-        rec['out'] = out
+            out, out_pl = _bn_apply(y2, m2, r2, P[p + '.bn2.weight'], P[p + '.bn2.bias'], b['final_relu'],
+                                    c2.rows_out, c2.Co, st, res=cur, res_planes=cur_op if tc else None,
+                                    want_rows=want_rows, want_planes=want_planes)
+        rec['out'], rec['out_hi'] = out, (out_pl[0] if out_pl else None)
         if need_ctx:
             ctx['blocks'].append(rec)
         cur, dims, C = out, c2.dims_out, b['planes']
-        if bi + 1 < len(spec):                       # the last block's output feeds the head, not a conv
-            cur_op = opnd(cur)
+        cur_op = out_pl if tc else out
     return cur, dims, (ctx if need_ctx else None)
 
 
@@ -304,48 +347,59 @@ def backbone_backward(ctx, dout, P):
         c1, c2 = rec['c1'], rec['c2']
         relu = b['final_relu']
         has_ds = b['downsample']
-        dy2, G[p + '.bn2.weight'], G[p + '.bn2.bias'], g = _bn_bwd(
+        tc = rec['tc']
+        kw = dict(want_rows=not tc, want_planes=tc)          # conv-operand format of the dy tensors
+        op = (lambda rows, planes: planes) if tc else (lambda rows, planes: rows)
+        dy2r, dy2p, G[p + '.bn2.weight'], G[p + '.bn2.bias'], g = _bn_bwd(
             dout, rec['out'], relu, rec['y2'], rec['m2'], rec['r2'], P[p + '.bn2.weight'],
-            c2.rows_out, c2.Co, st, want_g=not has_ds)
+            c2.rows_out, c2.Co, st, want_g=not has_ds, out_hi=rec['out_hi'], **kw)
+        dy2 = op(dy2r, dy2p)
         if has_ds:
             cd = rec['cd']
-            dyd, G[p + '.downsample.1.weight'], G[p + '.downsample.1.bias'], _ = _bn_bwd(
+            dydr, dydp, G[p + '.downsample.1.weight'], G[p + '.downsample.1.bias'], _ = _bn_bwd(
                 dout, rec['out'], relu, rec['yd'], rec['md'], rec['rd'], P[p + '.downsample.1.weight'],
-                cd.rows_out, cd.Co, st)
+                cd.rows_out, cd.Co, st, out_hi=rec['out_hi'], **kw)
+            dyd = op(dydr, dydp)
         del dout
-        opnd = (lambda t: _split(t, st)) if rec['tc'] else (lambda t: t)
-        dy2 = opnd(dy2)
         G[p + '.conv2.weight'] = c2.wgrad(rec['a1_op'], dy2, st)
         da1 = c2.dgrad(dy2, st)
-        del dy2
-        dy1, G[p + '.bn1.weight'], G[p + '.bn1.bias'], _ = _bn_bwd(
+        del dy2, dy2r, dy2p
+        dy1r, dy1p, G[p + '.bn1.weight'], G[p + '.bn1.bias'], _ = _bn_bwd(
             da1, rec['a1'], True, rec['y1'], rec['m1'], rec['r1'], P[p + '.bn1.weight'],
-            c1.rows_out, c1.Co, st)
+            c1.rows_out, c1.Co, st, out_hi=(rec['a1_op'][0] if tc else None), **kw)
+        dy1 = op(dy1r, dy1p)
         del da1
-        dy1 = opnd(dy1)
         G[p + '.conv1.weight'] = c1.wgrad(rec['xin_op'], dy1, st)
         if has_ds:
-            dyd = opnd(dyd)
             dx = c1.dgrad(dy1, st)
             cd.dgrad(dyd, st, dx=dx)
             G[p + '.downsample.0.weight'] = cd.wgrad(rec['xin_op'], dyd, st)
-            del dyd
+            del dyd, dydr, dydp
         else:
             dx = c1.dgrad(dy1, st, dx=g)          # dx = g + dgrad
-        del dy1
+        del dy1, dy1r, dy1p
         dout = dx
         rec.clear()
     NB, T, H, W, Ho, Wo = ctx['stem_dims']
     rows0 = NB * T * Ho * Wo
-    g0 = torch.empty_like(ctx['y0'])
-    _timed('stem_pool_bwd')(L.bn_relu_maxpool_bwd)(ptr(ctx['y0']), ptr(ctx['m0']), ptr(ctx['r0']), ptr(P['bn1.weight']),
-                          ptr(P['bn1.bias']), ptr(ctx['a0']), ptr(dout), ptr(g0), NB * T, Ho, Wo, 64, st)
+    # max-pool bwd + ReLU bwd + bn1 bwd fused: the 5.4 GB (B=128) gradient on the conv1 grid is never stored
+    tc = USE_TC
+    y0 = ctx['y0']
+    dy0 = None if tc else torch.empty_like(y0)
+    dy0p = (torch.empty(y0.shape, dtype=torch.bfloat16, device=y0.device),
+            torch.empty(y0.shape, dtype=torch.bfloat16, device=y0.device)) if tc else (None, None)
+    ws = torch.empty(128, dtype=torch.float64, device=y0.device)
+    G['bn1.weight'], G['bn1.bias'] = _empty((64,), y0), _empty((64,), y0)
+    _timed('stem_tail_bwd')(L.stem_tail_bwd)(ptr(y0), ptr(ctx['m0']), ptr(ctx['r0']), ptr(P['bn1.weight']),
+                                             ptr(P['bn1.bias']), ptr(ctx['a0']), ptr(dout), ptr(ws),
+                                             ptr(G['bn1.weight']), ptr(G['bn1.bias']), ptr(dy0), ptr(dy0p[0]),
+                                             ptr(dy0p[1]), NB * T, Ho, Wo, 64, st)
     del dout
-    dy0, G['bn1.weight'], G['bn1.bias'], _ = _bn_bwd(g0, None, False, ctx['y0'], ctx['m0'], ctx['r0'],
-                                                    P['bn1.weight'], rows0, 64, st)
-    del g0
     dw0 = torch.empty_like(P['conv1.weight'])
-    _timed('stem_wgrad')(L.stem_conv_wgrad)(ptr(ctx['x']), ptr(dy0), ptr(dw0), NB, T, H, W, st)
+    if tc:
+        _timed('stem_wgrad')(L.stem_conv_wgrad_tc)(ptr(ctx['x']), ptr(dy0p[0]), ptr(dy0p[1]), ptr(dw0), NB, T, H, W, st)
+    else:
+        _timed('stem_wgrad')(L.stem_conv_wgrad)(ptr(ctx['x']), ptr(dy0), ptr(dw0), NB, T, H, W, st)
     G['conv1.weight'] = dw0
     return G
 

@@ -66,9 +66,11 @@ int dpc_pack_conv_weight_bf16(const float* w, void* wf_hi, void* wf_lo, void* wd
 /* C[M,N] (+)= A[M,K] * B[N,K]^T, fp32 out, K % 64 == 0 */
 int dpc_gemm_nt_bf16x3_tc(int M, int N, int K, const void* a_hi, const void* a_lo, const void* b_hi,
                           const void* b_lo, float* C, int accumulate, void* stream);
-/* forward, strides in {1,2}: y = conv(x planes [NB,Ti,Hi,Wi,Ci], wf planes [Co][taps][Ci]) */
+/* forward, strides in {1,2}: y = conv(x planes [NB,Ti,Hi,Wi,Ci], wf planes [Co][taps][Ci]).
+ * bn_ws (nullable, 2*Co doubles): the epilogue also accumulates the per-channel sum / sum of squares of y
+ * (the BatchNorm batch statistics), to be turned into mean / rstd by dpc_bn_finalize. */
 int dpc_conv3d_fwd_tc(const dpc_conv_geom* g, const void* x_hi, const void* x_lo, const void* wf_hi,
-                      const void* wf_lo, float* y, void* stream);
+                      const void* wf_lo, float* y, double* bn_ws, void* stream);
 /* dgrad: dx (+)= conv^T(dy planes [NB,To,Ho,Wo,Co], wd planes [Ci][taps][Co]); one launch per
  * input-parity class of a strided site */
 int dpc_conv3d_dgrad_tc(const dpc_conv_geom* g, const void* dy_hi, const void* dy_lo, const void* wd_hi,
@@ -83,23 +85,37 @@ int dpc_stem_conv_fwd(const float* x, const float* w /*[64,3,1,7,7]*/, float* y,
                       int NB, int T, int H, int W, void* stream);
 int dpc_stem_conv_wgrad(const float* x, const float* dy, float* dw /*[64,3,1,7,7]*/,
                         int NB, int T, int H, int W, void* stream);
+/* tcgen05 versions (3xBF16 split; the im2col tile is built in shared memory from the fp32 video).
+ * bn_ws (nullable, 128 doubles) receives the per-channel sum | sum of squares of y (bn1 statistics). */
+int dpc_stem_conv_fwd_tc(const float* x, const float* w, float* y, double* bn_ws, int NB, int T, int H, int W,
+                         void* stream);
+/* dw [64,3,1,7,7] from the video and the split-bf16 planes of dy [NB,T,H/2,W/2,64] */
+int dpc_stem_conv_wgrad_tc(const float* x, const void* dy_hi, const void* dy_lo, float* dw, int NB, int T,
+                           int H, int W, void* stream);
 
 /* ---- BatchNorm3d(track_running_stats=False): batch statistics always ----------------------
  * replaces nn.BatchNorm3d at resnet_2d3d.py:55,59,91,95,212,243 (+ relu_ / `out += residual`
  * at :68-78,:104-114).  Biased variance, eps as given (1e-5).  `ws` = 2*C doubles of scratch. */
 int dpc_bn_stats(const float* y, int64_t rows, int C, double* ws, float* mean, float* rstd,
                  float eps, void* stream);
-/* out = [relu]( bn(y) + residual ), residual = none | res | bn_r(res)  (downsample branch) */
+int dpc_bn_finalize(const double* ws, int64_t rows, int C, float eps, float* mean, float* rstd, void* stream);
+/* out = [relu]( bn(y) + residual ), residual = none | res | bn_r(res)  (downsample branch).
+ * The raw residual may be fp32 rows (`res`) or split-bf16 planes (`res_hi/res_lo`); the result is written
+ * as fp32 rows (`out`, nullable) and/or split-bf16 planes (`out_hi/out_lo`, nullable) -- the
+ * tensor-core operand format, so no separate conversion pass is needed. */
 int dpc_bn_apply_fwd(const float* y, const float* mean, const float* rstd, const float* gamma,
-                     const float* beta, const float* res, const float* r_mean, const float* r_rstd,
-                     const float* r_gamma, const float* r_beta, int relu, float* out,
-                     int64_t rows, int C, void* stream);
+                     const float* beta, const float* res, const void* res_hi, const void* res_lo,
+                     const float* r_mean, const float* r_rstd, const float* r_gamma, const float* r_beta,
+                     int relu, float* out, void* out_hi, void* out_lo, int64_t rows, int C, void* stream);
 /* backward of the above for ONE BatchNorm: g = dout * (out > 0 if relu), then
  * dgamma = sum g*xhat, dbeta = sum g, dy = gamma*rstd*(g - dbeta/n - xhat*dgamma/n).
- * g_out (nullable) receives g (the gradient of the identity residual). `ws` = 2*C doubles. */
-int dpc_bn_bwd(const float* dout, const float* out, int relu, const float* y, const float* mean,
-               const float* rstd, const float* gamma, double* ws, float* dgamma, float* dbeta,
-               float* dy, float* g_out, int64_t rows, int C, void* stream);
+ * The ReLU mask comes from `out` (fp32 rows) or `out_hi` (the hi plane).  dy is written as fp32 rows
+ * and/or split-bf16 planes.  g_out (nullable) receives g (the gradient of the identity residual).
+ * `ws` = 2*C doubles. */
+int dpc_bn_bwd(const float* dout, const float* out, const void* out_hi, int relu, const float* y,
+               const float* mean, const float* rstd, const float* gamma, double* ws, float* dgamma,
+               float* dbeta, float* dy, void* dy_hi, void* dy_lo, float* g_out, int64_t rows, int C,
+               void* stream);
 
 /* ---- stem tail: BN + ReLU + MaxPool3d((1,3,3),s(1,2,2),p(0,1,1)) in one pass ---------------
  * replaces resnet_2d3d.py:212-214,261-263.  y [NB*T,H,W,C] -> out [NB*T,H/2,W/2,C]. */
@@ -109,6 +125,13 @@ int dpc_bn_relu_maxpool_fwd(const float* y, const float* mean, const float* rstd
 int dpc_bn_relu_maxpool_bwd(const float* y, const float* mean, const float* rstd, const float* gamma,
                             const float* beta, const float* out, const float* dout, float* g,
                             int NT, int H, int W, int C, void* stream);
+
+/* the whole stem tail backward in two passes (no materialised g): max-pool bwd + ReLU bwd + bn1 bwd.
+ * dout lives on the pooled grid; dy (fp32 rows and/or split-bf16 planes) on the conv1 output grid. */
+int dpc_stem_tail_bwd(const float* y, const float* mean, const float* rstd, const float* gamma,
+                      const float* beta, const float* out, const float* dout, double* ws, float* dgamma,
+                      float* dbeta, float* dy, void* dy_hi, void* dy_lo, int NT, int H, int W, int C,
+                      void* stream);
 
 /* ---- temporal average + ReLU split --------------------------------------------------------
  * replaces F.avg_pool3d / self.relu at dpc/model_3d.py:53-57.  z [NB,T,S,C] ->

@@ -94,11 +94,29 @@ def test_stem_conv(NB, T, H, W):
     yref = F.conv3d(xr, wr, None, (1, 2, 2), (0, 3, 3))
     assert tuple(yref.shape[2:]) == (T, Ho, Wo)
     assert rel(from_rows(y, NB, T, Ho, Wo), yref) < 2e-5
+    # tensor-core version + fused bn1 statistics
+    y2 = torch.full_like(y, float('nan'))
+    ws = torch.empty(128, dtype=torch.float64, device='cuda')
+    L.stem_conv_fwd_tc(x.data_ptr(), w.data_ptr(), y2.data_ptr(), ws.data_ptr(), NB, T, H, W, _st())
+    torch.cuda.synchronize()
+    assert not torch.isnan(y2).any()
+    assert rel(from_rows(y2, NB, T, Ho, Wo), yref) < 5e-5
+    mean, rstd = torch.empty(64, device='cuda'), torch.empty(64, device='cuda')
+    L.bn_finalize(ws.data_ptr(), y2.shape[0], 64, 1e-5, mean.data_ptr(), rstd.data_ptr(), _st())
+    assert float((mean - y2.double().mean(0)).abs().max()) < 1e-5 * float(y2.abs().max())
+    assert rel(rstd, 1 / torch.sqrt(y2.double().var(0, unbiased=False) + 1e-5)) < 1e-5
     dy = torch.randn(yref.shape, device='cuda', generator=g)
     yref.backward(dy)
     dw = torch.empty_like(w)
     L.stem_conv_wgrad(x.data_ptr(), to_rows(dy).data_ptr(), dw.data_ptr(), NB, T, H, W, _st())
     assert rel(dw, wr.grad) < 5e-5
+    from dpc_b200 import engine as E
+    dyp = E._split(to_rows(dy), _st())
+    dw2 = torch.full_like(w, float('nan'))
+    L.stem_conv_wgrad_tc(x.data_ptr(), dyp[0].data_ptr(), dyp[1].data_ptr(), dw2.data_ptr(), NB, T, H, W, _st())
+    torch.cuda.synchronize()
+    assert not torch.isnan(dw2).any()
+    assert rel(dw2, wr.grad) < 5e-5
 
 
 @pytest.mark.parametrize('C,rows', [(64, 5000), (128, 1237), (256, 96)])
@@ -123,29 +141,58 @@ def test_bn_fwd_bwd(C, rows, mode, relu):
     grr, brr = gr.clone().requires_grad_(True), br.clone().requires_grad_(True)
     ref = F.batch_norm(yr, None, None, gam, bet, True, 0.0, 1e-5)
     if mode == 'plain':
-        out = E._bn_apply(y, mean, rstd, gamma, beta, relu, rows, C, st)
+        out, _ = E._bn_apply(y, mean, rstd, gamma, beta, relu, rows, C, st)
     elif mode == 'res':
-        out = E._bn_apply(y, mean, rstd, gamma, beta, relu, rows, C, st, res=res)
+        out, _ = E._bn_apply(y, mean, rstd, gamma, beta, relu, rows, C, st, res=res)
         ref = ref + rr
     else:
         mr, sr = E._bn_stats(res, rows, C, st)
-        out = E._bn_apply(y, mean, rstd, gamma, beta, relu, rows, C, st, res=res, rbn=(mr, sr, gr, br))
+        out, _ = E._bn_apply(y, mean, rstd, gamma, beta, relu, rows, C, st, res=res, rbn=(mr, sr, gr, br))
         ref = ref + F.batch_norm(rr, None, None, grr, brr, True, 0.0, 1e-5)
     if relu:
         ref = F.relu(ref)
     assert rel(out, ref) < 1e-5
     dout = torch.randn(rows, C, device='cuda', generator=g)
     ref.backward(dout)
-    dy, dg, db, gbuf = E._bn_bwd(dout, out, relu, y, mean, rstd, gamma, rows, C, st, want_g=True)
+    dy, _, dg, db, gbuf = E._bn_bwd(dout, out, relu, y, mean, rstd, gamma, rows, C, st, want_g=True)
     assert rel(dy, yr.grad) < 5e-5
     assert rel(dg, gam.grad) < 5e-5
     assert rel(db, bet.grad) < 5e-5
     if mode == 'res':
         assert rel(gbuf, rr.grad) < 1e-6
     if mode == 'resbn':
-        dyr, dgr, dbr, _ = E._bn_bwd(dout, out, relu, res, mr, sr, gr, rows, C, st)
+        dyr, _, dgr, dbr, _ = E._bn_bwd(dout, out, relu, res, mr, sr, gr, rows, C, st)
         assert rel(dyr, rr.grad) < 5e-5
         assert rel(dgr, grr.grad) < 5e-5
+
+
+def test_bn_plane_io_matches_row_io():
+    """the fused split-bf16 plane outputs / plane residual / hi-plane ReLU mask agree with the fp32-row path"""
+    from dpc_b200 import engine as E
+    rows, C = 3000, 128
+    g = torch.Generator(device='cuda').manual_seed(33)
+    y = torch.randn(rows, C, device='cuda', generator=g) * 2 + 0.3
+    gamma = torch.rand(C, device='cuda', generator=g) + 0.5
+    beta = torch.randn(C, device='cuda', generator=g) * 0.1
+    res = torch.randn(rows, C, device='cuda', generator=g)
+    st = _st()
+    mean, rstd = E._bn_stats(y, rows, C, st)
+    ref, _ = E._bn_apply(y, mean, rstd, gamma, beta, True, rows, C, st, res=res)
+    resp = E._split(res, st)
+    out, pl = E._bn_apply(y, mean, rstd, gamma, beta, True, rows, C, st, res_planes=resp, want_rows=True, want_planes=True)
+    assert rel(out, ref) < 2e-5                                   # residual read through planes: ~2^-17
+    rec = pl[0].float() + pl[1].float()
+    assert rel(rec, out) < 2e-5
+    assert torch.equal(pl[0], out.to(torch.bfloat16))
+    hi2, lo2 = E._split(out, st)
+    assert torch.equal(hi2, pl[0]) and torch.equal(lo2, pl[1])    # same rounding as the stand-alone split kernel
+    dout = torch.randn(rows, C, device='cuda', generator=g)
+    dy, _, dg, db, gb = E._bn_bwd(dout, out, True, y, mean, rstd, gamma, rows, C, st, want_g=True)
+    _, dyp, dg2, db2, gb2 = E._bn_bwd(dout, None, True, y, mean, rstd, gamma, rows, C, st, want_g=True, out_hi=pl[0],
+                                      want_rows=False, want_planes=True)
+    assert torch.equal(gb, gb2)                                   # identical ReLU mask from the hi plane
+    assert rel(dg2, dg) < 1e-6 and rel(db2, db) < 1e-6            # (fp64 atomics: summation order varies)
+    assert rel(dyp[0].float() + dyp[1].float(), dy) < 2e-5
 
 
 @pytest.mark.parametrize('NT,H,W', [(6, 32, 32), (3, 16, 24), (2, 7, 9)])
@@ -178,10 +225,20 @@ def test_bn_relu_maxpool(NT, H, W):
     L.bn_relu_maxpool_bwd(y.data_ptr(), mean.data_ptr(), rstd.data_ptr(), gamma.data_ptr(), beta.data_ptr(),
                           out.data_ptr(), dout.data_ptr(), gbuf.data_ptr(), NT, H, W, C, st)
     # gbuf = grad wrt bn(y) output (ReLU mask applied); compare through the BN backward
-    dy, dg, db, _ = E._bn_bwd(gbuf, None, False, y, mean, rstd, gamma, NT * H * W, C, st)
+    dy, _, dg, db, _ = E._bn_bwd(gbuf, None, False, y, mean, rstd, gamma, NT * H * W, C, st)
     dy_ref = yr.grad.squeeze(2).permute(0, 2, 3, 1).reshape(-1, C)
     assert rel(dy, dy_ref) < 5e-5
     assert rel(dg, gam.grad) < 5e-5
+    # fused stem tail backward (no materialised g)
+    ws = torch.empty(2 * C, dtype=torch.float64, device='cuda')
+    dg2, db2, dy2 = torch.empty(C, device='cuda'), torch.empty(C, device='cuda'), torch.empty_like(y)
+    hi = torch.empty(y.shape, dtype=torch.bfloat16, device='cuda')
+    lo = torch.empty_like(hi)
+    L.stem_tail_bwd(y.data_ptr(), mean.data_ptr(), rstd.data_ptr(), gamma.data_ptr(), beta.data_ptr(), out.data_ptr(),
+                    dout.data_ptr(), ws.data_ptr(), dg2.data_ptr(), db2.data_ptr(), dy2.data_ptr(), hi.data_ptr(),
+                    lo.data_ptr(), NT, H, W, C, st)
+    assert rel(dy2, dy_ref) < 5e-5 and rel(dg2, gam.grad) < 5e-5 and rel(db2, bet.grad) < 5e-5
+    assert rel(hi.float() + lo.float(), dy2) < 2e-5
 
 
 def test_pool_split():

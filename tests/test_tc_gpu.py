@@ -118,8 +118,14 @@ def test_conv_fwd_dgrad_wgrad_tc(case):
     xh, xl = split(to_rows(x))
     geom = ConvGeom(NB, T, H, W, Ci, To, Ho, Wo, Co, k[0], k[1], k[2], s[0], s[1], s[2], p[0], p[1], p[2])
     y = torch.full((NB * To * Ho * Wo, Co), float('nan'), device='cuda')
-    L.conv3d_fwd_tc(geom, xh.data_ptr(), xl.data_ptr(), wfh.data_ptr(), wfl.data_ptr(), y.data_ptr(), _st())
+    ws = torch.empty(2 * Co, dtype=torch.float64, device='cuda')
+    L.conv3d_fwd_tc(geom, xh.data_ptr(), xl.data_ptr(), wfh.data_ptr(), wfl.data_ptr(), y.data_ptr(), ws.data_ptr(), _st())
     torch.cuda.synchronize()
+    # fused BatchNorm statistics of the conv output
+    mean, rstd = torch.empty(Co, device='cuda'), torch.empty(Co, device='cuda')
+    L.bn_finalize(ws.data_ptr(), y.shape[0], Co, 1e-5, mean.data_ptr(), rstd.data_ptr(), _st())
+    assert rel(mean, y.double().mean(0)) < 1e-5 or float((mean - y.mean(0)).abs().max()) < 1e-6
+    assert rel(rstd, 1 / torch.sqrt(y.double().var(0, unbiased=False) + 1e-5)) < 1e-5
     xr = x.clone().requires_grad_(True)
     wr = w.clone().requires_grad_(True)
     yref = F.conv3d(xr, wr, None, s, p)
