@@ -316,6 +316,56 @@ __device__ __forceinline__ float4 stem_pool_grad(float4 v /* relu(bn(y)) pre-act
     return acc;
 }
 
+// One thread owns a 2x2 block of conv1-grid positions (x one channel quad): the four positions share the
+// four pooling windows (ho in {h2, h2+1}) x (wo in {w2, w2+1}), so out/dout are loaded once per block
+// (12 vector loads per 4 positions instead of 22).
+struct TailBlock {
+    float4 yv[4];      // y at (2h2+a, 2w2+b), index a*2+b
+    float4 g[4];       // gradient w.r.t. bn(y) at those positions
+    bool ok[4];
+};
+__device__ __forceinline__ void tail_block(TailBlock& tb, const float* __restrict__ y, const Affine4& a,
+                                           const float* __restrict__ out, const float* __restrict__ dout, long long nt,
+                                           int h2, int w2, int H, int W, int Ho, int Wo, int C, int cq) {
+    float4 p[4], d[4];
+    bool wok[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int ho = h2 + (i >> 1), wo = w2 + (i & 1);
+        wok[i] = ho < Ho && wo < Wo;
+        if (wok[i]) {
+            const long long o = ((nt * Ho + ho) * Wo + wo) * C + cq * 4;
+            p[i] = ld4(out + o); d[i] = ld4(dout + o);
+        } else {
+            p[i] = make_float4(-1.f, -1.f, -1.f, -1.f); d[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int aa = i >> 1, bb = i & 1;
+        const int h = 2 * h2 + aa, w = 2 * w2 + bb;
+        tb.ok[i] = h < H && w < W;
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (tb.ok[i]) {
+            tb.yv[i] = ld4(y + ((nt * H + h) * W + w) * C + cq * 4);
+            const float4 v = affine(tb.yv[i], a);
+            // windows containing (h, w): ho = h2 (+1 if the row is odd), wo = w2 (+1 if the column is odd)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int dh = j >> 1, dw = j & 1;
+                if ((dh && !aa) || (dw && !bb)) continue;
+                if (v.x > 0.f && v.x == p[j].x) acc.x += d[j].x;
+                if (v.y > 0.f && v.y == p[j].y) acc.y += d[j].y;
+                if (v.z > 0.f && v.z == p[j].z) acc.z += d[j].z;
+                if (v.w > 0.f && v.w == p[j].w) acc.w += d[j].w;
+            }
+        } else {
+            tb.yv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        tb.g[i] = acc;
+    }
+}
+
 __global__ void __launch_bounds__(THREADS) stem_tail_bwd_reduce_kernel(
     const float* __restrict__ y, const float* mean, const float* rstd, const float* gamma, const float* beta,
     const float* __restrict__ out, const float* __restrict__ dout, int NT, int H, int W, int Ho, int Wo, int C,
@@ -324,20 +374,25 @@ __global__ void __launch_bounds__(THREADS) stem_tail_bwd_reduce_kernel(
     const int cq = threadIdx.x % C4, rl = threadIdx.x / C4;
     const Affine4 a = make_affine(mean, rstd, gamma, beta, cq * 4);
     const float4 m = ld4(mean + cq * 4), rs = ld4(rstd + cq * 4);
-    const long long rows = (long long)NT * H * W;
+    const int H2 = (H + 1) / 2, W2 = (W + 1) / 2;
+    const long long blocks = (long long)NT * H2 * W2;
     double s[4] = {0, 0, 0, 0}, sx[4] = {0, 0, 0, 0};
-    const long long chunk = (long long)STRIP * rg;
-    for (long long base = (long long)blockIdx.x * chunk; base < rows; base += (long long)gridDim.x * chunk) {
+    const long long chunk = (long long)(STRIP / 4) * rg;           // 16 blocks = 64 positions per fp32 strip
+    for (long long base = (long long)blockIdx.x * chunk; base < blocks; base += (long long)gridDim.x * chunk) {
         float4 pa = make_float4(0.f, 0.f, 0.f, 0.f), pb = pa;
-        long long end = base + chunk < rows ? base + chunk : rows;
+        long long end = base + chunk < blocks ? base + chunk : blocks;
         for (long long r = base + rl; r < end; r += rg) {
-            const int w = (int)(r % W), h = (int)((r / W) % H);
-            const long long nt = r / ((long long)W * H);
-            const float4 yv = ld4(y + r * C + cq * 4);
-            const float4 g = stem_pool_grad(affine(yv, a), out, dout, nt, h, w, Ho, Wo, C, cq);
-            pa.x += g.x; pa.y += g.y; pa.z += g.z; pa.w += g.w;
-            pb.x = fmaf(g.x, (yv.x - m.x) * rs.x, pb.x); pb.y = fmaf(g.y, (yv.y - m.y) * rs.y, pb.y);
-            pb.z = fmaf(g.z, (yv.z - m.z) * rs.z, pb.z); pb.w = fmaf(g.w, (yv.w - m.w) * rs.w, pb.w);
+            const int w2 = (int)(r % W2), h2 = (int)((r / W2) % H2);
+            const long long nt = r / ((long long)W2 * H2);
+            TailBlock tb;
+            tail_block(tb, y, a, out, dout, nt, h2, w2, H, W, Ho, Wo, C, cq);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float4 g = tb.g[i], yv = tb.yv[i];          // g == 0 where the position is out of range
+                pa.x += g.x; pa.y += g.y; pa.z += g.z; pa.w += g.w;
+                pb.x = fmaf(g.x, (yv.x - m.x) * rs.x, pb.x); pb.y = fmaf(g.y, (yv.y - m.y) * rs.y, pb.y);
+                pb.z = fmaf(g.z, (yv.z - m.z) * rs.z, pb.z); pb.w = fmaf(g.w, (yv.w - m.w) * rs.w, pb.w);
+            }
         }
         s[0] += pa.x; s[1] += pa.y; s[2] += pa.z; s[3] += pa.w;
         sx[0] += pb.x; sx[1] += pb.y; sx[2] += pb.z; sx[3] += pb.w;
@@ -354,25 +409,32 @@ __global__ void __launch_bounds__(THREADS) stem_tail_bwd_apply_kernel(
     const int c = cq * 4;
     const Affine4 a = make_affine(mean, rstd, gamma, beta, c);
     const float4 m = ld4(mean + c), rs = ld4(rstd + c), ga = ld4(gamma + c);
-    const long long rows = (long long)NT * H * W;
-    const double inv_n = 1.0 / (double)rows;
+    const double inv_n = 1.0 / ((double)NT * H * W);
     float mb[4], mg[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) { mb[i] = (float)(ws[c + i] * inv_n); mg[i] = (float)(ws[C + c + i] * inv_n); }
     const float k0 = ga.x * rs.x, k1 = ga.y * rs.y, k2 = ga.z * rs.z, k3 = ga.w * rs.w;
-    for (long long r = (long long)blockIdx.x * rg + rl; r < rows; r += (long long)gridDim.x * rg) {
-        const int w = (int)(r % W), h = (int)((r / W) % H);
-        const long long nt = r / ((long long)W * H);
-        const long long off = r * C + c;
-        const float4 yv = ld4(y + off);
-        const float4 g = stem_pool_grad(affine(yv, a), out, dout, nt, h, w, Ho, Wo, C, cq);
-        float4 d;
-        d.x = k0 * (g.x - mb[0] - (yv.x - m.x) * rs.x * mg[0]);
-        d.y = k1 * (g.y - mb[1] - (yv.y - m.y) * rs.y * mg[1]);
-        d.z = k2 * (g.z - mb[2] - (yv.z - m.z) * rs.z * mg[2]);
-        d.w = k3 * (g.w - mb[3] - (yv.w - m.w) * rs.w * mg[3]);
-        if (dy) st4(dy + off, d);
-        if (dy_hi) st4_planes(dy_hi, dy_lo, off, d);
+    const int H2 = (H + 1) / 2, W2 = (W + 1) / 2;
+    const long long blocks = (long long)NT * H2 * W2;
+    for (long long r = (long long)blockIdx.x * rg + rl; r < blocks; r += (long long)gridDim.x * rg) {
+        const int w2 = (int)(r % W2), h2 = (int)((r / W2) % H2);
+        const long long nt = r / ((long long)W2 * H2);
+        TailBlock tb;
+        tail_block(tb, y, a, out, dout, nt, h2, w2, H, W, Ho, Wo, C, cq);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            if (!tb.ok[i]) continue;
+            const int h = 2 * h2 + (i >> 1), w = 2 * w2 + (i & 1);
+            const long long off = ((nt * H + h) * W + w) * C + c;
+            const float4 g = tb.g[i], yv = tb.yv[i];
+            float4 d;
+            d.x = k0 * (g.x - mb[0] - (yv.x - m.x) * rs.x * mg[0]);
+            d.y = k1 * (g.y - mb[1] - (yv.y - m.y) * rs.y * mg[1]);
+            d.z = k2 * (g.z - mb[2] - (yv.z - m.z) * rs.z * mg[2]);
+            d.w = k3 * (g.w - mb[3] - (yv.w - m.w) * rs.w * mg[3]);
+            if (dy) st4(dy + off, d);
+            if (dy_hi) st4_planes(dy_hi, dy_lo, off, d);
+        }
     }
 }
 
@@ -540,17 +602,18 @@ extern "C" int dpc_stem_tail_bwd(const float* y, const float* mean, const float*
     cudaStream_t st = as_stream(stream);
     const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
     const int C4 = C / 4, rg = THREADS / C4;
-    const long long rows = (long long)NT * H * W;
+    const long long blocks = (long long)NT * ((H + 1) / 2) * ((W + 1) / 2);
     DPC_CUDA(cudaMemsetAsync(ws, 0, sizeof(double) * 2 * C, st));
-    long long chunks = (rows + (long long)STRIP * rg - 1) / ((long long)STRIP * rg);
+    const long long per = (long long)(STRIP / 4) * rg;
+    long long chunks = (blocks + per - 1) / per;
     int grid = (int)(chunks < (long long)dpc_num_sms() * 8 ? chunks : (long long)dpc_num_sms() * 8);
     size_t smem = sizeof(double) * (size_t)rg * C4 * 8;
     stem_tail_bwd_reduce_kernel<<<grid, THREADS, smem, st>>>(y, mean, rstd, gamma, beta, out, dout, NT, H, W, Ho, Wo, C, ws);
     DPC_LAUNCH_CHECK();
     bn_bwd_finalize_kernel<<<ceil_div(C, 128), 128, 0, st>>>(ws, C, dgamma, dbeta);
     DPC_LAUNCH_CHECK();
-    stem_tail_bwd_apply_kernel<<<stream_grid(rows, rg), THREADS, 0, st>>>(y, mean, rstd, gamma, beta, out, dout, NT, H, W,
-                                                                          Ho, Wo, C, ws, dy, dy_hi, dy_lo);
+    stem_tail_bwd_apply_kernel<<<stream_grid(blocks, rg), THREADS, 0, st>>>(y, mean, rstd, gamma, beta, out, dout, NT, H, W,
+                                                                            Ho, Wo, C, ws, dy, dy_hi, dy_lo);
     DPC_LAUNCH_CHECK();
     return DPC_OK;
 }

@@ -93,7 +93,7 @@ __device__ __forceinline__ uint32_t setup_common(const SmemPlan& sp, const uint8
 // =============================================================================================
 // forward / dgrad / plain GEMM:  out[position, co] = sum_{tap, c} G[position (+) tap, c] * Wp[co][tap][c]
 // =============================================================================================
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(192, 2)
 conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p, float* __restrict__ y, int accumulate,
                double* __restrict__ stats) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -250,7 +250,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p, float* __r
 //   same [positions x 64 channels] TMA boxes.  grid = (co tiles * ci tiles, taps, splits);
 //   partial sums are reduced with fp32 atomics.
 // =============================================================================================
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(192, 2)
 wgrad_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p, float* __restrict__ dwp) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     const SmemPlan sp = plan_smem(smem_raw, p.BN, p.stages);
@@ -434,6 +434,10 @@ void set_stages(TcLaunch& L, int num_kb) {
     TcParams& p = L.p;
     const int stage_bytes = 2 * A_TILE_BYTES + 2 * p.BN * 128;
     int stages = (200 * 1024) / stage_bytes;
+    // Narrow tiles (BN <= 64: layer1 / its gradients) have only ~9 k-blocks per tile, so the tile prologue and
+    // epilogue dominate a one-CTA-per-SM schedule.  Two co-resident CTAs per SM (2 stages of 48 KB each)
+    // let one CTA's epilogue overlap the other's MMA main loop.
+    if (p.BN <= 64) stages = 2;
     if (stages > 6) stages = 6;
     if (stages > num_kb) stages = num_kb;
     if (stages < 1) stages = 1;
