@@ -90,6 +90,73 @@ __device__ __forceinline__ uint32_t setup_common(const SmemPlan& sp, const uint8
     return *reinterpret_cast<const uint32_t*>(smem_raw + (sp.tmem_ptr() - smem_u32(smem_raw)));
 }
 
+// One warp's share of a finished tile: TMEM lanes [32q, 32q+32) = tile rows; adds the two accumulators,
+// stores the fp32 rows, and (optionally) accumulates the BatchNorm partial sums of the tile.
+__device__ __forceinline__ void tile_epilogue(const TcParams& p, float* __restrict__ y, int accumulate,
+                                              float* stat_smem, uint32_t tmem_d, uint32_t tmem_c, int q, int lane,
+                                              int n0, int t0, int h0, int w0, int ncol0) {
+    const int r = q * 32 + lane;
+    const int dw = r % p.bw, dh = (r / p.bw) % p.bh, dt = (r / (p.bw * p.bh)) % p.bt, dn = r / (p.bw * p.bh * p.bt);
+    const int n = n0 + dn, t = t0 + dt, h = h0 + dh, w = w0 + dw;
+    const bool valid = r < p.box_rows && n < p.NB && t < p.To && h < p.Ho && w < p.Wo;
+    const long long row = (long long)n * p.out_sn + (long long)t * p.out_st + (long long)h * p.out_sh +
+                          (long long)w * p.out_sw + p.out_base;
+    float* yrow = y + row * p.Co + ncol0;
+    const bool vec = (p.Co & 3) == 0;
+    for (int c0 = 0; c0 < p.BN; c0 += 32) {
+        uint32_t v[32], u[32];
+        tmem_ld32(tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+        tmem_ld32(tmem_c + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, u);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(u[j]));
+        if (valid) {
+            if (vec && ncol0 + c0 + 32 <= p.Co) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    float4 o = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
+                                           __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+                    float4* dst = reinterpret_cast<float4*>(yrow + c0) + j;
+                    if (accumulate) { float4 c = *dst; o.x += c.x; o.y += c.y; o.z += c.z; o.w += c.w; }
+                    *dst = o;
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    if (ncol0 + c0 + j < p.Co) {
+                        float o = __uint_as_float(v[j]);
+                        if (accumulate) o += yrow[c0 + j];
+                        yrow[c0 + j] = o;
+                    }
+                }
+            }
+        }
+        if (stat_smem) {
+            // BatchNorm statistics of this tile, fused into the producer: per-column sum / sum of squares
+            // over the warp's 32 rows by a 31-shuffle transposing butterfly (lane l ends up with column
+            // c0+l), then shared-memory partials per CTA.
+            float sv[32], sq[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                const float f = valid ? __uint_as_float(v[j]) : 0.f;
+                sv[j] = f; sq[j] = f * f;
+            }
+#pragma unroll
+            for (int off = 16; off >= 1; off >>= 1) {
+                const bool up = (lane & off) != 0;
+#pragma unroll
+                for (int i = 0; i < off; ++i) {
+                    const float s_send = up ? sv[i] : sv[i + off], s_keep = up ? sv[i + off] : sv[i];
+                    const float q_send = up ? sq[i] : sq[i + off], q_keep = up ? sq[i + off] : sq[i];
+                    sv[i] = s_keep + __shfl_xor_sync(0xffffffffu, s_send, off);
+                    sq[i] = q_keep + __shfl_xor_sync(0xffffffffu, q_send, off);
+                }
+            }
+            atomicAdd(&stat_smem[c0 + lane], sv[0]);
+            atomicAdd(&stat_smem[256 + c0 + lane], sq[0]);
+        }
+    }
+}
+
 // =============================================================================================
 // forward / dgrad / plain GEMM:  out[position, co] = sum_{tap, c} G[position (+) tap, c] * Wp[co][tap][c]
 // =============================================================================================
@@ -167,69 +234,9 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p, float* __r
         }
     } else {
         // epilogue: warps 2..5; TMEM lane quarter = warp % 4
-        const int q = warp & 3;
-        const int r = q * 32 + lane;
-        const int dw = r % p.bw, dh = (r / p.bw) % p.bh, dt = (r / (p.bw * p.bh)) % p.bt, dn = r / (p.bw * p.bh * p.bt);
-        const int n = n0 + dn, t = t0 + dt, h = h0 + dh, w = w0 + dw;
-        const bool valid = r < p.box_rows && n < p.NB && t < p.To && h < p.Ho && w < p.Wo;
-        const long long row = (long long)n * p.out_sn + (long long)t * p.out_st + (long long)h * p.out_sh +
-                              (long long)w * p.out_sw + p.out_base;
-        float* yrow = y + row * p.Co + ncol0;
         mbar_wait(sp.tmem_full(), 0);
         tc_fence_after();
-        const bool vec = (p.Co & 3) == 0;
-        for (int c0 = 0; c0 < p.BN; c0 += 32) {
-            uint32_t v[32], u[32];
-            tmem_ld32(tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
-            tmem_ld32(tmem_c + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, u);
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(u[j]));
-            if (valid) {
-                if (vec && ncol0 + c0 + 32 <= p.Co) {
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        float4 o = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
-                                               __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
-                        float4* dst = reinterpret_cast<float4*>(yrow + c0) + j;
-                        if (accumulate) { float4 c = *dst; o.x += c.x; o.y += c.y; o.z += c.z; o.w += c.w; }
-                        *dst = o;
-                    }
-                } else {
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        if (ncol0 + c0 + j < p.Co) {
-                            float o = __uint_as_float(v[j]);
-                            if (accumulate) o += yrow[c0 + j];
-                            yrow[c0 + j] = o;
-                        }
-                    }
-                }
-            }
-            if (stats) {
-                // BatchNorm statistics of this tile, fused into the producer: per-column sum / sum of
-                // squares over the warp's 32 rows by a 31-shuffle transposing butterfly (lane l ends up
-                // with column c0+l), then shared-memory partials per CTA.
-                float sv[32], sq[32];
-#pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    const float f = valid ? __uint_as_float(v[j]) : 0.f;
-                    sv[j] = f; sq[j] = f * f;
-                }
-#pragma unroll
-                for (int off = 16; off >= 1; off >>= 1) {
-                    const bool up = (lane & off) != 0;
-#pragma unroll
-                    for (int i = 0; i < off; ++i) {
-                        const float s_send = up ? sv[i] : sv[i + off], s_keep = up ? sv[i + off] : sv[i];
-                        const float q_send = up ? sq[i] : sq[i + off], q_keep = up ? sq[i + off] : sq[i];
-                        sv[i] = s_keep + __shfl_xor_sync(0xffffffffu, s_send, off);
-                        sq[i] = q_keep + __shfl_xor_sync(0xffffffffu, q_send, off);
-                    }
-                }
-                atomicAdd(&stat_smem[c0 + lane], sv[0]);
-                atomicAdd(&stat_smem[256 + c0 + lane], sq[0]);
-            }
-        }
+        tile_epilogue(p, y, accumulate, stats ? stat_smem : nullptr, tmem_d, tmem_c, warp & 3, lane, n0, t0, h0, w0, ncol0);
     }
     tc_fence_before();
     __syncthreads();
@@ -239,6 +246,163 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p, float* __r
             if (ncol0 + c < p.Co) {
                 atomicAdd(stats + ncol0 + c, (double)stat_smem[c]);
                 atomicAdd(stats + p.Co + ncol0 + c, (double)stat_smem[256 + c]);
+            }
+        }
+    }
+}
+
+// =============================================================================================
+// Persistent variant for narrow outputs (BN <= 128, one N tile): each CTA walks many tiles, the TMEM
+// accumulators are double-buffered so the epilogue of tile i overlaps the MMAs of tile i+1, and -- when the
+// whole packed filter bank fits (layer1: 9 taps x 64 x 64 x hi/lo = 144 KB) -- the weights stay RESIDENT
+// in shared memory instead of being re-fetched from L2 for every tile (layer1 is L2-bandwidth bound).
+// =============================================================================================
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+
+__global__ void __launch_bounds__(192, 1)
+conv_tc_persist_kernel(const __grid_constant__ TcMaps maps, const TcParams p, float* __restrict__ y, int accumulate,
+                       double* __restrict__ stats, int resident_b, int total_tiles) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int ntaps = p.tT.count * p.tH.count * p.tW.count;
+    const int num_kb = ntaps * p.cchunks;
+    const uint32_t b_tile = (uint32_t)p.BN * 128u;
+    // smem: [resident weights: num_kb x (hi | lo)] [stages x (A_hi | A_lo [| B_hi | B_lo])] [barriers] [stats]
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t w_bytes = resident_b ? (uint32_t)num_kb * 2u * b_tile : 0u;
+    const uint32_t stage_bytes = 2u * A_TILE_BYTES + (resident_b ? 0u : 2u * b_tile);
+    const uint32_t ring = base + w_bytes;
+    const uint32_t bar_base = ring + (uint32_t)p.stages * stage_bytes;
+    auto full = [&](int s) { return bar_base + 8u * s; };
+    auto empty = [&](int s) { return bar_base + 8u * (p.stages + s); };
+    const uint32_t w_full = bar_base + 8u * (2 * p.stages);
+    auto tm_full = [&](int b) { return bar_base + 8u * (2 * p.stages + 1 + b); };
+    auto tm_empty = [&](int b) { return bar_base + 8u * (2 * p.stages + 3 + b); };
+    const uint32_t tmem_ptr_addr = bar_base + 8u * (2 * p.stages + 5);
+    float* stat_smem = reinterpret_cast<float*>(smem_raw + (bar_base + 8u * (2 * p.stages + 6) - smem_u32(smem_raw)));
+    if (stats)
+        for (int i = threadIdx.x; i < 512; i += blockDim.x) stat_smem[i] = 0.f;
+    const uint32_t tmem_cols = 4u * (uint32_t)p.BN;            // 2 buffers x (main + cross-term) accumulators
+    if (warp == 0 && lane == 0) {
+        for (int v = 0; v < p.nviews; ++v) {
+            asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.a_hi[v]) : "memory");
+            asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.a_lo[v]) : "memory");
+        }
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.b_hi) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.b_lo) : "memory");
+        for (int s = 0; s < p.stages; ++s) { mbar_init(full(s), 1); mbar_init(empty(s), 1); }
+        mbar_init(w_full, 1);
+        for (int b = 0; b < 2; ++b) { mbar_init(tm_full(b), 1); mbar_init(tm_empty(b), 4); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) tmem_alloc(tmem_ptr_addr, tmem_cols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *reinterpret_cast<const uint32_t*>(smem_raw + (tmem_ptr_addr - smem_u32(smem_raw)));
+    const int my_tiles = ((int)blockIdx.x < total_tiles) ? (total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+
+    auto tile_origin = [&](int i, int& n0, int& t0, int& h0, int& w0) {
+        int tile = (int)blockIdx.x + i * (int)gridDim.x;
+        const int tw = tile % p.tiles_w; tile /= p.tiles_w;
+        const int th = tile % p.tiles_h; tile /= p.tiles_h;
+        const int tt = tile % p.tiles_t; tile /= p.tiles_t;
+        w0 = tw * p.bw; h0 = th * p.bh; t0 = tt * p.bt; n0 = tile * p.bn;
+    };
+
+    if (warp == 0) {
+        if (elect_one()) {
+            if (resident_b && my_tiles > 0) {
+                mbar_expect_tx(w_full, w_bytes);
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    const int tap = kb / p.cchunks, cc = kb - tap * p.cchunks;
+                    const int iw = tap % p.tW.count, ih = (tap / p.tW.count) % p.tH.count, it = tap / (p.tW.count * p.tH.count);
+                    const int tap_full = (p.tT.k[it] * p.kH + p.tH.k[ih]) * p.kW + p.tW.k[iw];
+                    const int kcol = tap_full * p.Ksrc + cc * 64;
+                    tma_load_2d(&maps.b_hi, base + (uint32_t)kb * 2u * b_tile, w_full, kcol, 0);
+                    tma_load_2d(&maps.b_lo, base + (uint32_t)kb * 2u * b_tile + b_tile, w_full, kcol, 0);
+                }
+            }
+            const uint32_t tx = 2u * (uint32_t)(p.box_rows * 128) + (resident_b ? 0u : 2u * b_tile);
+            int s = 0; uint32_t ph = 0;
+            for (int i = 0; i < my_tiles; ++i) {
+                int n0, t0, h0, w0;
+                tile_origin(i, n0, t0, h0, w0);
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    const int tap = kb / p.cchunks, cc = kb - tap * p.cchunks;
+                    const int iw = tap % p.tW.count, ih = (tap / p.tW.count) % p.tH.count, it = tap / (p.tW.count * p.tH.count);
+                    const int view = (p.tT.par[it] * p.sH + p.tH.par[ih]) * p.sW + p.tW.par[iw];
+                    mbar_wait(empty(s), ph ^ 1u);
+                    mbar_expect_tx(full(s), tx);
+                    const uint32_t sa = ring + s * stage_bytes;
+                    const int cw = w0 + p.tW.off[iw], chh = h0 + p.tH.off[ih], ct = t0 + p.tT.off[it];
+                    tma_load_5d(&maps.a_hi[view], sa, full(s), cc * 64, cw, chh, ct, n0);
+                    tma_load_5d(&maps.a_lo[view], sa + A_TILE_BYTES, full(s), cc * 64, cw, chh, ct, n0);
+                    if (!resident_b) {
+                        const int tap_full = (p.tT.k[it] * p.kH + p.tH.k[ih]) * p.kW + p.tW.k[iw];
+                        const int kcol = tap_full * p.Ksrc + cc * 64;
+                        tma_load_2d(&maps.b_hi, sa + 2 * A_TILE_BYTES, full(s), kcol, 0);
+                        tma_load_2d(&maps.b_lo, sa + 2 * A_TILE_BYTES + b_tile, full(s), kcol, 0);
+                    }
+                    if (++s == p.stages) { s = 0; ph ^= 1u; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (elect_one()) {
+            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.BN >> 3) << 17) | ((128u >> 4) << 24);
+            if (resident_b && my_tiles > 0) mbar_wait(w_full, 0);
+            int s = 0; uint32_t ph = 0;
+            for (int i = 0; i < my_tiles; ++i) {
+                const int buf = i & 1;
+                const uint32_t td = tmem_base + (uint32_t)(buf * 2 * p.BN), tcx = td + (uint32_t)p.BN;
+                mbar_wait(tm_empty(buf), (((uint32_t)i >> 1) & 1u) ^ 1u);        // epilogue drained this buffer
+                tc_fence_after();
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    mbar_wait(full(s), ph);
+                    tc_fence_after();
+                    const uint32_t sa = ring + s * stage_bytes;
+                    const uint32_t sb = resident_b ? base + (uint32_t)kb * 2u * b_tile : sa + 2 * A_TILE_BYTES;
+                    const uint64_t ahi = make_kmajor_sw128_desc(sa), alo = make_kmajor_sw128_desc(sa + A_TILE_BYTES);
+                    const uint64_t bhi = make_kmajor_sw128_desc(sb), blo = make_kmajor_sw128_desc(sb + b_tile);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const uint64_t ko = (uint64_t)(k * 2);
+                        umma_bf16(td, ahi + ko, bhi + ko, idesc, (kb | k) ? 1u : 0u);
+                        umma_bf16(tcx, ahi + ko, blo + ko, idesc, (kb | k) ? 1u : 0u);
+                        umma_bf16(tcx, alo + ko, bhi + ko, idesc, 1u);
+                    }
+                    umma_commit(empty(s));
+                    if (++s == p.stages) { s = 0; ph ^= 1u; }
+                }
+                umma_commit(tm_full(buf));
+            }
+        }
+    } else {
+        const int q = warp & 3;
+        for (int i = 0; i < my_tiles; ++i) {
+            const int buf = i & 1;
+            const uint32_t td = tmem_base + (uint32_t)(buf * 2 * p.BN), tcx = td + (uint32_t)p.BN;
+            int n0, t0, h0, w0;
+            tile_origin(i, n0, t0, h0, w0);
+            mbar_wait(tm_full(buf), ((uint32_t)i >> 1) & 1u);
+            tc_fence_after();
+            tile_epilogue(p, y, accumulate, stats ? stat_smem : nullptr, td, tcx, q, lane, n0, t0, h0, w0, 0);
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tm_empty(buf));
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, tmem_cols);
+    if (stats) {
+        for (int c = threadIdx.x; c < p.BN; c += blockDim.x) {
+            if (c < p.Co) {
+                atomicAdd(stats + c, (double)stat_smem[c]);
+                atomicAdd(stats + p.Co + c, (double)stat_smem[256 + c]);
             }
         }
     }
@@ -504,6 +668,30 @@ int make_parity_views(TcMaps& maps, const dpc_conv_geom* g, const void* x_hi, co
 }
 
 int launch_conv(TcLaunch& L, float* y, int accumulate, cudaStream_t st, double* stats = nullptr) {
+    const TcParams& p = L.p;
+    const int total_tiles = (int)L.grid.x;
+    const int sms = dpc_num_sms();
+    if (p.BN <= 128 && L.grid.y == 1 && p.Co <= p.BN && total_tiles >= 2 * sms) {
+        // persistent schedule: double-buffered TMEM, resident weights when they fit
+        const int num_kb = p.tT.count * p.tH.count * p.tW.count * p.cchunks;
+        const size_t b_tile = (size_t)p.BN * 128;
+        const size_t w_bytes = (size_t)num_kb * 2 * b_tile;
+        const size_t budget = 220 * 1024;
+        const int resident = (w_bytes + 2 * (2 * A_TILE_BYTES) + 4096 <= budget) ? 1 : 0;
+        const size_t stage_bytes = 2 * A_TILE_BYTES + (resident ? 0 : 2 * b_tile);
+        int stages = (int)((budget - 4096 - (resident ? w_bytes : 0)) / stage_bytes);
+        if (stages > 6) stages = 6;
+        if (stages >= 2) {
+            TcParams pp = p;
+            pp.stages = stages;
+            const size_t smem = (resident ? w_bytes : 0) + (size_t)stages * stage_bytes + 8 * (2 * stages + 6) + 2048 + 1024;
+            DPC_CUDA(cudaFuncSetAttribute(conv_tc_persist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            const int grid = total_tiles < sms ? total_tiles : sms;
+            conv_tc_persist_kernel<<<grid, 192, smem, st>>>(L.maps, pp, y, accumulate, stats, resident, total_tiles);
+            DPC_LAUNCH_CHECK();
+            return DPC_OK;
+        }
+    }
     DPC_CUDA(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smem));
     conv_tc_kernel<<<L.grid, 192, L.smem, st>>>(L.maps, L.p, y, accumulate, stats);
     DPC_LAUNCH_CHECK();

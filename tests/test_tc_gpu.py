@@ -94,6 +94,12 @@ CASES = [
     (4, 3, 8, 8, 256, 256, (3, 3, 3), (2, 2, 2), (1, 1, 1)),        # layer4.0.conv1
     (3, 3, 7, 7, 256, 256, (3, 3, 3), (2, 2, 2), (1, 1, 1)),        # odd extents
     (2, 5, 28, 28, 64, 128, (1, 3, 3), (1, 2, 2), (0, 1, 1)),
+    # >= 2 tiles per SM with narrow outputs: the persistent kernel (resident / streamed weights)
+    (8, 5, 32, 32, 64, 64, (1, 3, 3), (1, 1, 1), (0, 1, 1)),
+    (32, 5, 16, 16, 128, 128, (1, 3, 3), (1, 1, 1), (0, 1, 1)),
+    (32, 5, 32, 32, 64, 128, (1, 3, 3), (1, 2, 2), (0, 1, 1)),
+    (32, 5, 32, 32, 64, 128, (1, 1, 1), (1, 2, 2), (0, 0, 0)),
+    (9, 5, 30, 30, 64, 64, (1, 3, 3), (1, 1, 1), (0, 1, 1)),
 ]
 
 
