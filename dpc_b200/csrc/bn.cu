@@ -366,7 +366,7 @@ __device__ __forceinline__ void tail_block(TailBlock& tb, const float* __restric
     }
 }
 
-__global__ void __launch_bounds__(THREADS) stem_tail_bwd_reduce_kernel(
+__global__ void __launch_bounds__(THREADS, 3) stem_tail_bwd_reduce_kernel(
     const float* __restrict__ y, const float* mean, const float* rstd, const float* gamma, const float* beta,
     const float* __restrict__ out, const float* __restrict__ dout, int NT, int H, int W, int Ho, int Wo, int C,
     double* __restrict__ ws) {
@@ -400,7 +400,7 @@ __global__ void __launch_bounds__(THREADS) stem_tail_bwd_reduce_kernel(
     block_reduce_atomic(s, sx, cq, rl, C4, rg, ws, C);
 }
 
-__global__ void __launch_bounds__(THREADS) stem_tail_bwd_apply_kernel(
+__global__ void __launch_bounds__(THREADS, 3) stem_tail_bwd_apply_kernel(
     const float* __restrict__ y, const float* mean, const float* rstd, const float* gamma, const float* beta,
     const float* __restrict__ out, const float* __restrict__ dout, int NT, int H, int W, int Ho, int Wo, int C,
     const double* __restrict__ ws, float* __restrict__ dy, void* __restrict__ dy_hi, void* __restrict__ dy_lo) {

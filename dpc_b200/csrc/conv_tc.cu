@@ -46,6 +46,7 @@ struct TcParams {
     long long out_sn, out_st, out_sh, out_sw, out_base;   // output row = n*sn + t*st + h*sh + w*sw + base
     // wgrad only
     int taps_full, splits, ktiles_per_split;
+    int tap_group;             // taps per CTA (they share the dY tile; N = tap_group * BN)
 };
 
 constexpr int A_TILE_BYTES = 128 * 128;            // 128 rows x 64 bf16
@@ -417,9 +418,10 @@ conv_tc_persist_kernel(const __grid_constant__ TcMaps maps, const TcParams p, fl
 __global__ void __launch_bounds__(192, 2)
 wgrad_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p, float* __restrict__ dwp) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
-    const SmemPlan sp = plan_smem(smem_raw, p.BN, p.stages);
+    const int NG = p.BN * p.tap_group;                        // accumulator width: tap_group taps side by side
+    const SmemPlan sp = plan_smem(smem_raw, NG, p.stages);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t tmem_cols = 2u * (p.BN < 16 ? 16 : p.BN);   // main + correction accumulators
+    const uint32_t tmem_cols = 2u * (NG < 16 ? 16 : NG);      // main + correction accumulators
     // Position boxes may hold fewer than a multiple of 16 rows (UMMA_K): rows the TMA never writes
     // must read as zero, so clear the operand stages once (generic proxy), then hand over to the
     // async proxy (TMA / UMMA).
@@ -430,28 +432,28 @@ wgrad_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p, float* __
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
     const uint32_t tmem_d = setup_common(sp, smem_raw, maps, p.nviews, tmem_cols);
-    const uint32_t tmem_c = tmem_d + (uint32_t)p.BN;
+    const uint32_t tmem_c = tmem_d + (uint32_t)NG;
 
     const int ci_tiles = (p.Ksrc + p.BN - 1) / p.BN;
     const int co0 = (blockIdx.x / ci_tiles) * 128, ci0 = (blockIdx.x % ci_tiles) * p.BN;
-    // this CTA's tap
-    const int tap = blockIdx.y;
-    const int iw = tap % p.tW.count, ih = (tap / p.tW.count) % p.tH.count, it = tap / (p.tW.count * p.tH.count);
-    const int tap_full = (p.tT.k[it] * p.kH + p.tH.k[ih]) * p.kW + p.tW.k[iw];
-    const int view = (p.tT.par[it] * p.sH + p.tH.par[ih]) * p.sW + p.tW.par[iw];
+    // this CTA's taps: [tap_beg, tap_beg + gt).  They share the dY tile (A operand); their shifted X tiles
+    // sit side by side in the B operand, so one MMA of width gt*BN covers all of them.
+    const int ntaps = p.tT.count * p.tH.count * p.tW.count;
+    const int tap_beg = blockIdx.y * p.tap_group;
+    const int gt = (ntaps - tap_beg) < p.tap_group ? (ntaps - tap_beg) : p.tap_group;
     const int total_tiles = p.tiles_w * p.tiles_h * p.tiles_t * p.tiles_n;
     const int kt_beg = blockIdx.z * p.ktiles_per_split;
     int kt_end = kt_beg + p.ktiles_per_split;
     if (kt_end > total_tiles) kt_end = total_tiles;
     const int num_kb = kt_end - kt_beg;
-    const int nb_groups = p.BN / 64;              // 64-channel groups of the B operand
+    const int nb_groups = p.BN / 64;              // 64-channel groups per tap in the B operand
     const uint32_t box_bytes = (uint32_t)p.box_rows * 128u;   // one [positions x 64ch] box (<= 8 KB)
     const uint32_t GROUP = 8192u;                 // smem distance between 64-channel groups (64 rows * 128 B)
 
     if (num_kb > 0) {
         if (warp == 0) {
             if (elect_one()) {
-                const uint32_t tx = 2u * 2u * box_bytes + 2u * (uint32_t)nb_groups * box_bytes;
+                const uint32_t tx = 2u * 2u * box_bytes + 2u * (uint32_t)(gt * nb_groups) * box_bytes;
                 int s = 0; uint32_t ph = 0;
                 for (int kb = 0; kb < num_kb; ++kb) {
                     int tile = kt_beg + kb;
@@ -467,21 +469,27 @@ wgrad_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p, float* __
                         tma_load_5d(&maps.b_hi, sa + g * GROUP, sp.full(s), co0 + g * 64, w0, h0, t0, n0);
                         tma_load_5d(&maps.b_lo, sa + A_TILE_BYTES + g * GROUP, sp.full(s), co0 + g * 64, w0, h0, t0, n0);
                     }
-                    // B = X at the tap-shifted positions (parity view)
-                    const int cw = w0 + p.tW.off[iw], chh = h0 + p.tH.off[ih], ct = t0 + p.tT.off[it];
-                    for (int g = 0; g < nb_groups; ++g) {
-                        tma_load_5d(&maps.a_hi[view], sa + 2 * A_TILE_BYTES + g * GROUP, sp.full(s), ci0 + g * 64, cw, chh, ct, n0);
-                        tma_load_5d(&maps.a_lo[view], sa + 2 * A_TILE_BYTES + sp.b_tile_bytes + g * GROUP, sp.full(s),
-                                    ci0 + g * 64, cw, chh, ct, n0);
+                    // B = X at the tap-shifted positions (parity view), one block of 64-channel groups per tap
+                    for (int j = 0; j < gt; ++j) {
+                        const int tap = tap_beg + j;
+                        const int iw = tap % p.tW.count, ih = (tap / p.tW.count) % p.tH.count, it = tap / (p.tW.count * p.tH.count);
+                        const int view = (p.tT.par[it] * p.sH + p.tH.par[ih]) * p.sW + p.tW.par[iw];
+                        const int cw = w0 + p.tW.off[iw], chh = h0 + p.tH.off[ih], ct = t0 + p.tT.off[it];
+                        for (int g = 0; g < nb_groups; ++g) {
+                            const uint32_t off = (uint32_t)(j * nb_groups + g) * GROUP;
+                            tma_load_5d(&maps.a_hi[view], sa + 2 * A_TILE_BYTES + off, sp.full(s), ci0 + g * 64, cw, chh, ct, n0);
+                            tma_load_5d(&maps.a_lo[view], sa + 2 * A_TILE_BYTES + sp.b_tile_bytes + off, sp.full(s),
+                                        ci0 + g * 64, cw, chh, ct, n0);
+                        }
                     }
                     if (++s == p.stages) { s = 0; ph ^= 1u; }
                 }
             }
         } else if (warp == 1) {
             if (elect_one()) {
-                // D=f32, A=B=bf16, both MN-major (bits 15,16), N = BN, M = 128
+                // D=f32, A=B=bf16, both MN-major (bits 15,16), N = gt*BN, M = 128
                 const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) |
-                                       ((uint32_t)(p.BN >> 3) << 17) | ((128u >> 4) << 24);
+                                       ((uint32_t)((gt * p.BN) >> 3) << 17) | ((128u >> 4) << 24);
                 const int ksteps = (p.box_rows + 15) / 16;  // UMMA_K = 16 positions; rows past the box are zero
                 int s = 0; uint32_t ph = 0;
                 for (int kb = 0; kb < num_kb; ++kb) {
@@ -507,17 +515,21 @@ wgrad_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p, float* __
             const int co = co0 + q * 32 + lane;             // D row = output channel
             mbar_wait(sp.tmem_full(), 0);
             tc_fence_after();
-            float* orow = dwp + ((size_t)co * p.taps_full + tap_full) * p.Ksrc + ci0;
-            for (int c0 = 0; c0 < p.BN; c0 += 32) {
+            for (int c0 = 0; c0 < gt * p.BN; c0 += 32) {
+                const int j = c0 / p.BN, cin = c0 - j * p.BN;
+                const int tap = tap_beg + j;
+                const int iw = tap % p.tW.count, ih = (tap / p.tW.count) % p.tH.count, it = tap / (p.tW.count * p.tH.count);
+                const int tap_full = (p.tT.k[it] * p.kH + p.tH.k[ih]) * p.kW + p.tW.k[iw];
                 uint32_t v[32], u[32];
                 tmem_ld32(tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
                 tmem_ld32(tmem_c + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, u);
 #pragma unroll
-                for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(u[j]));
+                for (int jj = 0; jj < 32; ++jj) v[jj] = __float_as_uint(__uint_as_float(v[jj]) + __uint_as_float(u[jj]));
                 if (co >= p.Co) continue;
+                float* orow = dwp + ((size_t)co * p.taps_full + tap_full) * p.Ksrc + ci0 + cin;
 #pragma unroll
-                for (int j = 0; j < 32; ++j)
-                    if (ci0 + c0 + j < p.Ksrc) atomicAdd(orow + c0 + j, __uint_as_float(v[j]));
+                for (int jj = 0; jj < 32; ++jj)
+                    if (ci0 + cin + jj < p.Ksrc) atomicAdd(orow + jj, __uint_as_float(v[jj]));
             }
         }
     }
@@ -902,8 +914,13 @@ extern "C" int dpc_conv3d_wgrad_tc(const dpc_conv_geom* g, const void* x_hi, con
     set_tile_grid(p, g->NB, g->To, g->Ho, g->Wo, 64);           // K-block = up to 64 output positions
     p.Co = g->Co; p.BN = pick_bn(g->Ci);
     p.taps_full = taps;
+    // narrow inputs: several taps share one CTA (and one dY tile); their accumulators sit side by side (N <= 256)
+    p.tap_group = 256 / p.BN;
+    if (p.tap_group > taps) p.tap_group = taps;
+    if (p.tap_group < 1) p.tap_group = 1;
+    const int tap_groups = (taps + p.tap_group - 1) / p.tap_group;
     const int total_tiles = p.tiles_w * p.tiles_h * p.tiles_t * p.tiles_n;
-    const int work = ((g->Co + 127) / 128) * ((g->Ci + p.BN - 1) / p.BN) * taps;
+    const int work = ((g->Co + 127) / 128) * ((g->Ci + p.BN - 1) / p.BN) * tap_groups;
     int splits = (2 * dpc_num_sms() + work - 1) / work;
     if (splits < 1) splits = 1;
     if (splits > total_tiles) splits = total_tiles;
@@ -914,14 +931,19 @@ extern "C" int dpc_conv3d_wgrad_tc(const dpc_conv_geom* g, const void* x_hi, con
     splits = (total_tiles + p.ktiles_per_split - 1) / p.ktiles_per_split;
     DPC_REQUIRE(splits <= 65535, "dpc_conv3d_wgrad_tc: too many K splits (%d)", splits);
     p.splits = splits;
-    set_stages(L, p.ktiles_per_split);
+    {
+        const int bn = p.BN;
+        p.BN = bn * p.tap_group;               // stage sizing uses the grouped width
+        set_stages(L, p.ktiles_per_split);
+        p.BN = bn;
+    }
     const uint32_t box[5] = {64, (uint32_t)p.bw, (uint32_t)p.bh, (uint32_t)p.bt, (uint32_t)p.bn};
     if (int rc = make_parity_views(L.maps, g, x_hi, x_lo, box)) return rc;
     const long long sw = g->Co, sh = (long long)g->Wo * sw, sT = (long long)g->Ho * sh, sn = (long long)g->To * sT;
     if (int rc = make_act_map(&L.maps.b_hi, dy_hi, g->Co, g->Wo, g->Ho, g->To, g->NB, sw, sh, sT, sn, box)) return rc;
     if (int rc = make_act_map(&L.maps.b_lo, dy_lo, g->Co, g->Wo, g->Ho, g->To, g->NB, sw, sh, sT, sn, box)) return rc;
     DPC_CUDA(cudaMemsetAsync(dwp, 0, sizeof(float) * (size_t)g->Co * taps * g->Ci, st));
-    L.grid = dim3((unsigned)(((g->Co + 127) / 128) * ((g->Ci + p.BN - 1) / p.BN)), (unsigned)taps, (unsigned)splits);
+    L.grid = dim3((unsigned)(((g->Co + 127) / 128) * ((g->Ci + p.BN - 1) / p.BN)), (unsigned)tap_groups, (unsigned)splits);
     DPC_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smem));
     wgrad_tc_kernel<<<L.grid, 192, L.smem, st>>>(L.maps, L.p, dwp);
     DPC_LAUNCH_CHECK();

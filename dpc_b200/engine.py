@@ -336,10 +336,38 @@ def backbone_forward(network, x, P, need_ctx=True):
     return cur, dims, (ctx if need_ctx else None)
 
 
+# Weight gradients are leaves of the backward graph: nothing on the dgrad -> BN-backward chain waits for
+# them.  They run on a side stream so the tensor-bound wgrad kernels overlap the HBM-bound BN-backward
+# passes of the following layers (one side stream per device, joined before backward returns).
+_SIDE_STREAMS = {}
+OVERLAP_WGRAD = True
+
+
+def _side_stream(device):
+    s = _SIDE_STREAMS.get(device)
+    if s is None:
+        s = _SIDE_STREAMS[device] = torch.cuda.Stream(device=device)
+    return s
+
+
+def _wgrad_async(site, x_op, dy_op, main, side):
+    """site.wgrad(x_op, dy_op) on the side stream, ordered after everything issued so far on `main`"""
+    if side is None:
+        return site.wgrad(x_op, dy_op, main.cuda_stream)
+    side.wait_stream(main)
+    with torch.cuda.stream(side):
+        dw = site.wgrad(x_op, dy_op, side.cuda_stream)
+    for t in (x_op if isinstance(x_op, tuple) else (x_op,)) + (dy_op if isinstance(dy_op, tuple) else (dy_op,)):
+        t.record_stream(side)          # the caching allocator must not recycle these before the side stream is done
+    return dw
+
+
 def backbone_backward(ctx, dout, P):
     """dout: rows [NB*To*Ho*Wo, 256].  Returns dict name -> grad (parameter layouts)."""
     L = lib()
     st = _stream()
+    main = torch.cuda.current_stream()
+    side = _side_stream(dout.device) if (OVERLAP_WGRAD and _TIMER is None) else None
     G = {}
     for rec in reversed(ctx['blocks']):
         b = rec['spec']
@@ -361,7 +389,7 @@ def backbone_backward(ctx, dout, P):
                 cd.rows_out, cd.Co, st, out_hi=rec['out_hi'], **kw)
             dyd = op(dydr, dydp)
         del dout
-        G[p + '.conv2.weight'] = c2.wgrad(rec['a1_op'], dy2, st)
+        G[p + '.conv2.weight'] = _wgrad_async(c2, rec['a1_op'], dy2, main, side)
         da1 = c2.dgrad(dy2, st)
         del dy2, dy2r, dy2p
         dy1r, dy1p, G[p + '.bn1.weight'], G[p + '.bn1.bias'], _ = _bn_bwd(
@@ -369,11 +397,11 @@ def backbone_backward(ctx, dout, P):
             c1.rows_out, c1.Co, st, out_hi=(rec['a1_op'][0] if tc else None), **kw)
         dy1 = op(dy1r, dy1p)
         del da1
-        G[p + '.conv1.weight'] = c1.wgrad(rec['xin_op'], dy1, st)
+        G[p + '.conv1.weight'] = _wgrad_async(c1, rec['xin_op'], dy1, main, side)
         if has_ds:
             dx = c1.dgrad(dy1, st)
             cd.dgrad(dyd, st, dx=dx)
-            G[p + '.downsample.0.weight'] = cd.wgrad(rec['xin_op'], dyd, st)
+            G[p + '.downsample.0.weight'] = _wgrad_async(cd, rec['xin_op'], dyd, main, side)
             del dyd, dydr, dydp
         else:
             dx = c1.dgrad(dy1, st, dx=g)          # dx = g + dgrad
@@ -401,6 +429,8 @@ def backbone_backward(ctx, dout, P):
     else:
         _timed('stem_wgrad')(L.stem_conv_wgrad)(ptr(ctx['x']), ptr(dy0), ptr(dw0), NB, T, H, W, st)
     G['conv1.weight'] = dw0
+    if side is not None:
+        main.wait_stream(side)
     return G
 
 
