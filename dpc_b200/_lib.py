@@ -44,7 +44,7 @@ _SIGS = {
     'dpc_bn_bwd': (c_int, [P, P, P, c_int, P, P, P, P, P, P, P, P, P, P, P, c_int64, c_int, P]),
     'dpc_bn_relu_maxpool_fwd': (c_int, [P, P, P, P, P, P, c_int, c_int, c_int, c_int, P]),
     'dpc_bn_relu_maxpool_bwd': (c_int, [P, P, P, P, P, P, P, P, c_int, c_int, c_int, c_int, P]),
-    'dpc_stem_tail_bwd': (c_int, [P, P, P, P, P, P, P, P, P, P, P, P, P, c_int, c_int, c_int, c_int, P]),
+    'dpc_stem_tail_bwd': (c_int, [P, P, P, P, P, P, P, P, P, P, P, P, P, c_int, c_int, c_int, c_int, c_int, P]),
     'dpc_pool_split_fwd':(c_int, [P, P, P, c_int, c_int, c_int, c_int, P]),
     'dpc_pool_split_bwd': (c_int, [P, P, P, P, c_int, c_int, c_int, c_int, P]),
     'dpc_gemm_f32': (c_int, [c_int, c_int, c_int, c_int, c_int, c_float, P, c_int, P, c_int, c_float, P, c_int, P]),

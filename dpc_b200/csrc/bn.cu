@@ -366,6 +366,38 @@ __device__ __forceinline__ void tail_block(TailBlock& tb, const float* __restric
     }
 }
 
+// The reduce pass on the POOLED grid (4x fewer elements, y is not read at all): the gradient of a pooling
+// window lands on its arg-max position, whose normalised value follows from the pooled output itself,
+//   a = gamma * xhat + beta  ->  xhat = (a - beta) / gamma            (a > 0: ReLU passed)
+// so  sum g = sum_w dout_w [a_w > 0]  and  sum g*xhat = sum_w dout_w [a_w > 0] (a_w - beta) / gamma.
+// (Requires gamma != 0; exact ties inside a window have measure zero.)
+__global__ void __launch_bounds__(THREADS) stem_tail_bwd_reduce_pooled_kernel(
+    const float* gamma, const float* beta, const float* __restrict__ out, const float* __restrict__ dout,
+    long long rows, int C, double* __restrict__ ws) {
+    const int C4 = C / 4, rg = THREADS / C4;
+    const int cq = threadIdx.x % C4, rl = threadIdx.x / C4;
+    const float4 ga = ld4(gamma + cq * 4), be = ld4(beta + cq * 4);
+    const float4 ig = make_float4(1.f / ga.x, 1.f / ga.y, 1.f / ga.z, 1.f / ga.w);
+    double s[4] = {0, 0, 0, 0}, sx[4] = {0, 0, 0, 0};
+    const long long chunk = (long long)STRIP * rg;
+    for (long long base = (long long)blockIdx.x * chunk; base < rows; base += (long long)gridDim.x * chunk) {
+        float4 pa = make_float4(0.f, 0.f, 0.f, 0.f), pb = pa;
+        long long end = base + chunk < rows ? base + chunk : rows;
+        for (long long r = base + rl; r < end; r += rg) {
+            const long long off = r * C + cq * 4;
+            const float4 a = ld4(out + off), d = ld4(dout + off);
+            const float gx = a.x > 0.f ? d.x : 0.f, gy = a.y > 0.f ? d.y : 0.f;
+            const float gz = a.z > 0.f ? d.z : 0.f, gw = a.w > 0.f ? d.w : 0.f;
+            pa.x += gx; pa.y += gy; pa.z += gz; pa.w += gw;
+            pb.x = fmaf(gx, (a.x - be.x) * ig.x, pb.x); pb.y = fmaf(gy, (a.y - be.y) * ig.y, pb.y);
+            pb.z = fmaf(gz, (a.z - be.z) * ig.z, pb.z); pb.w = fmaf(gw, (a.w - be.w) * ig.w, pb.w);
+        }
+        s[0] += pa.x; s[1] += pa.y; s[2] += pa.z; s[3] += pa.w;
+        sx[0] += pb.x; sx[1] += pb.y; sx[2] += pb.z; sx[3] += pb.w;
+    }
+    block_reduce_atomic(s, sx, cq, rl, C4, rg, ws, C);
+}
+
 __global__ void __launch_bounds__(THREADS, 3) stem_tail_bwd_reduce_kernel(
     const float* __restrict__ y, const float* mean, const float* rstd, const float* gamma, const float* beta,
     const float* __restrict__ out, const float* __restrict__ dout, int NT, int H, int W, int Ho, int Wo, int C,
@@ -593,7 +625,7 @@ extern "C" int dpc_bn_relu_maxpool_bwd(const float* y, const float* mean, const 
 extern "C" int dpc_stem_tail_bwd(const float* y, const float* mean, const float* rstd, const float* gamma,
                                  const float* beta, const float* out, const float* dout, double* ws, float* dgamma,
                                  float* dbeta, float* dy, void* dy_hi, void* dy_lo, int NT, int H, int W, int C,
-                                 void* stream) {
+                                 int pooled_reduce, void* stream) {
     DPC_REQUIRE(y && mean && rstd && gamma && beta && out && dout && ws && dgamma && dbeta && NT > 0,
                 "dpc_stem_tail_bwd: bad args");
     DPC_REQUIRE(dy || (dy_hi && dy_lo), "dpc_stem_tail_bwd: no output");
@@ -604,11 +636,18 @@ extern "C" int dpc_stem_tail_bwd(const float* y, const float* mean, const float*
     const int C4 = C / 4, rg = THREADS / C4;
     const long long blocks = (long long)NT * ((H + 1) / 2) * ((W + 1) / 2);
     DPC_CUDA(cudaMemsetAsync(ws, 0, sizeof(double) * 2 * C, st));
-    const long long per = (long long)(STRIP / 4) * rg;
-    long long chunks = (blocks + per - 1) / per;
-    int grid = (int)(chunks < (long long)dpc_num_sms() * 8 ? chunks : (long long)dpc_num_sms() * 8);
     size_t smem = sizeof(double) * (size_t)rg * C4 * 8;
-    stem_tail_bwd_reduce_kernel<<<grid, THREADS, smem, st>>>(y, mean, rstd, gamma, beta, out, dout, NT, H, W, Ho, Wo, C, ws);
+    if (pooled_reduce) {
+        const long long prow = (long long)NT * Ho * Wo;
+        long long chunks = (prow + (long long)STRIP * rg - 1) / ((long long)STRIP * rg);
+        int grid = (int)(chunks < (long long)dpc_num_sms() * 8 ? chunks : (long long)dpc_num_sms() * 8);
+        stem_tail_bwd_reduce_pooled_kernel<<<grid, THREADS, smem, st>>>(gamma, beta, out, dout, prow, C, ws);
+    } else {
+        const long long per = (long long)(STRIP / 4) * rg;
+        long long chunks = (blocks + per - 1) / per;
+        int grid = (int)(chunks < (long long)dpc_num_sms() * 8 ? chunks : (long long)dpc_num_sms() * 8);
+        stem_tail_bwd_reduce_kernel<<<grid, THREADS, smem, st>>>(y, mean, rstd, gamma, beta, out, dout, NT, H, W, Ho, Wo, C, ws);
+    }
     DPC_LAUNCH_CHECK();
     bn_bwd_finalize_kernel<<<ceil_div(C, 128), 128, 0, st>>>(ws, C, dgamma, dbeta);
     DPC_LAUNCH_CHECK();

@@ -17,6 +17,7 @@
 // Replaces nn.Conv3d fwd/bwd at backbone/resnet_2d3d.py:13-31,241-244 and torch.matmul at
 // dpc/model_3d.py:83.
 #include "tc_common.cuh"
+#include <stdlib.h>
 
 namespace {
 
@@ -425,7 +426,7 @@ wgrad_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p, float* __
     // Position boxes may hold fewer than a multiple of 16 rows (UMMA_K): rows the TMA never writes
     // must read as zero, so clear the operand stages once (generic proxy), then hand over to the
     // async proxy (TMA / UMMA).
-    {
+    if (p.box_rows & 15) {
         uint4* z = reinterpret_cast<uint4*>(smem_raw + (sp.base - smem_u32(smem_raw)));
         const int n16 = (int)((uint32_t)sp.stages * sp.stage_bytes / 16u);
         for (int i = threadIdx.x; i < n16; i += blockDim.x) z[i] = make_uint4(0u, 0u, 0u, 0u);
@@ -689,7 +690,10 @@ int launch_conv(TcLaunch& L, float* y, int accumulate, cudaStream_t st, double* 
         const size_t b_tile = (size_t)p.BN * 128;
         const size_t w_bytes = (size_t)num_kb * 2 * b_tile;
         const size_t budget = 220 * 1024;
-        const int resident = (w_bytes + 2 * (2 * A_TILE_BYTES) + 4096 <= budget) ? 1 : 0;
+        // resident weights only pay off if >= 4 activation stages still fit (measured: with 2 stages the TMA
+        // latency is exposed and streaming the weights through a deeper ring is faster)
+        int resident = (w_bytes + 4 * (2 * A_TILE_BYTES) + 4096 <= budget) ? 1 : 0;
+        if (const char* e = getenv("DPC_TC_RESIDENT")) resident = resident && atoi(e);     // tuning knob
         const size_t stage_bytes = 2 * A_TILE_BYTES + (resident ? 0 : 2 * b_tile);
         int stages = (int)((budget - 4096 - (resident ? w_bytes : 0)) / stage_bytes);
         if (stages > 6) stages = 6;
@@ -921,13 +925,27 @@ extern "C" int dpc_conv3d_wgrad_tc(const dpc_conv_geom* g, const void* x_hi, con
     const int tap_groups = (taps + p.tap_group - 1) / p.tap_group;
     const int total_tiles = p.tiles_w * p.tiles_h * p.tiles_t * p.tiles_n;
     const int work = ((g->Co + 127) / 128) * ((g->Ci + p.BN - 1) / p.BN) * tap_groups;
-    int splits = (2 * dpc_num_sms() + work - 1) / work;
-    if (splits < 1) splits = 1;
+    // K splits: one CTA per SM is resident, so pick the split count that wastes the least of the last wave
+    // (time ~ ceil(work*s / SMs) / s), among counts that leave >= 8 position tiles per CTA
+    int splits = 1;
+    {
+        const int sms = dpc_num_sms();
+        int s_lo = (sms + work - 1) / work, s_hi = (6 * sms + work - 1) / work;
+        if (s_hi > total_tiles / 8) s_hi = total_tiles / 8;
+        if (s_lo > s_hi) s_lo = s_hi;
+        if (s_lo < 1) s_lo = 1;
+        double best = 1e30;
+        for (int sp = s_lo; sp <= (s_hi > s_lo ? s_hi : s_lo); ++sp) {
+            const long long ctas = (long long)work * sp;
+            const double cost = (double)((ctas + sms - 1) / sms) / (double)sp;
+            if (cost < best * 0.98) { best = cost; splits = sp; }
+        }
+    }
     if (splits > total_tiles) splits = total_tiles;
     p.ktiles_per_split = (total_tiles + splits - 1) / splits;
     // bound the in-TMEM accumulation chain (truncating adds): <= 512 position tiles (2048 UMMA steps,
     // ~ -4e-5 relative); longer reductions continue through the fp32 (round-to-nearest) atomics
-    if (p.ktiles_per_split > 512) p.ktiles_per_split = 512;
+    if (p.ktiles_per_split > 512) p.ktiles_per_split = 512;   // (more, shorter CTAs measured slower: prologue + atomics)
     splits = (total_tiles + p.ktiles_per_split - 1) / p.ktiles_per_split;
     DPC_REQUIRE(splits <= 65535, "dpc_conv3d_wgrad_tc: too many K splits (%d)", splits);
     p.splits = splits;

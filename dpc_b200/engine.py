@@ -421,7 +421,7 @@ def backbone_backward(ctx, dout, P):
     _timed('stem_tail_bwd')(L.stem_tail_bwd)(ptr(y0), ptr(ctx['m0']), ptr(ctx['r0']), ptr(P['bn1.weight']),
                                              ptr(P['bn1.bias']), ptr(ctx['a0']), ptr(dout), ptr(ws),
                                              ptr(G['bn1.weight']), ptr(G['bn1.bias']), ptr(dy0), ptr(dy0p[0]),
-                                             ptr(dy0p[1]), NB * T, Ho, Wo, 64, st)
+                                             ptr(dy0p[1]), NB * T, Ho, Wo, 64, 1, st)
     del dout
     dw0 = torch.empty_like(P['conv1.weight'])
     if tc:

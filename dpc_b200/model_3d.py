@@ -72,8 +72,8 @@ class DPC_RNN(nn.Module):
         self._initialize_weights(self.network_pred)
 
     def _head_params(self):
-        sd = dict(self.named_parameters(remove_duplicate=False))
-        return [sd[n].contiguous() for n in engine.HEAD_PARAM_NAMES]
+        from .resnet_2d3d import get_tensor          # attribute walk: valid on nn.DataParallel replicas
+        return [get_tensor(self, n).contiguous() for n in engine.HEAD_PARAM_NAMES]
 
     def forward(self, block):
         # block: [B, N, C, SL, H, W]

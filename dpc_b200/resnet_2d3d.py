@@ -27,6 +27,14 @@ def conv1x3x3(in_planes, out_planes, stride=1, bias=False):         # resnet_2d3
                      padding=(0, 1, 1), bias=bias)
 
 
+def get_tensor(module, dotted):
+    """module.a.0.weight by attribute walk (works on nn.DataParallel replicas too)"""
+    obj = module
+    for part in dotted.split('.'):
+        obj = getattr(obj, part)
+    return obj
+
+
 class _BasicBlock(nn.Module):
     expansion = 1
     _conv = None
@@ -152,8 +160,9 @@ class ResNet2d3d_full(nn.Module):                                  # resnet_2d3d
         if not x.is_cuda:
             raise RuntimeError('dpc_b200 has no CPU path: input must be a CUDA tensor')
         x = x.contiguous().float()
-        sd = dict(self.named_parameters())
-        params = [sd[n].contiguous() for n in self._names]
+        # attribute walk, not named_parameters(): nn.DataParallel replicas hold their (non-leaf) parameter
+        # copies as plain attributes, so named_parameters() is empty there
+        params = [get_tensor(self, n).contiguous() for n in self._names]
         need = torch.is_grad_enabled() and any(p.requires_grad for p in params)
         rows = _BackboneFn.apply(x, self.network, self._names, need, *params)
         return rows, self.out_dims(x.shape[2], x.shape[3], x.shape[4])

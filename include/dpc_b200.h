@@ -127,11 +127,13 @@ int dpc_bn_relu_maxpool_bwd(const float* y, const float* mean, const float* rstd
                             int NT, int H, int W, int C, void* stream);
 
 /* the whole stem tail backward in two passes (no materialised g): max-pool bwd + ReLU bwd + bn1 bwd.
- * dout lives on the pooled grid; dy (fp32 rows and/or split-bf16 planes) on the conv1 output grid. */
+ * dout lives on the pooled grid; dy (fp32 rows and/or split-bf16 planes) on the conv1 output grid.
+ * pooled_reduce != 0: the reduction pass runs on the pooled grid only (xhat of each window's arg-max is
+ * recovered from the pooled output: needs gamma != 0 everywhere). */
 int dpc_stem_tail_bwd(const float* y, const float* mean, const float* rstd, const float* gamma,
                       const float* beta, const float* out, const float* dout, double* ws, float* dgamma,
                       float* dbeta, float* dy, void* dy_hi, void* dy_lo, int NT, int H, int W, int C,
-                      void* stream);
+                      int pooled_reduce, void* stream);
 
 /* ---- temporal average + ReLU split --------------------------------------------------------
  * replaces F.avg_pool3d / self.relu at dpc/model_3d.py:53-57.  z [NB,T,S,C] ->

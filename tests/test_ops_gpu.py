@@ -234,11 +234,12 @@ def test_bn_relu_maxpool(NT, H, W):
     dg2, db2, dy2 = torch.empty(C, device='cuda'), torch.empty(C, device='cuda'), torch.empty_like(y)
     hi = torch.empty(y.shape, dtype=torch.bfloat16, device='cuda')
     lo = torch.empty_like(hi)
-    L.stem_tail_bwd(y.data_ptr(), mean.data_ptr(), rstd.data_ptr(), gamma.data_ptr(), beta.data_ptr(), out.data_ptr(),
-                    dout.data_ptr(), ws.data_ptr(), dg2.data_ptr(), db2.data_ptr(), dy2.data_ptr(), hi.data_ptr(),
-                    lo.data_ptr(), NT, H, W, C, st)
-    assert rel(dy2, dy_ref) < 5e-5 and rel(dg2, gam.grad) < 5e-5 and rel(db2, bet.grad) < 5e-5
-    assert rel(hi.float() + lo.float(), dy2) < 2e-5
+    for pooled in (0, 1):
+        L.stem_tail_bwd(y.data_ptr(), mean.data_ptr(), rstd.data_ptr(), gamma.data_ptr(), beta.data_ptr(), out.data_ptr(),
+                        dout.data_ptr(), ws.data_ptr(), dg2.data_ptr(), db2.data_ptr(), dy2.data_ptr(), hi.data_ptr(),
+                        lo.data_ptr(), NT, H, W, C, pooled, st)
+        assert rel(dy2, dy_ref) < 5e-5 and rel(dg2, gam.grad) < 5e-5 and rel(db2, bet.grad) < 5e-5, pooled
+        assert rel(hi.float() + lo.float(), dy2) < 2e-5
 
 
 def test_pool_split():

@@ -223,3 +223,33 @@ def test_no_cpu_fallback():
         m = dpc_b200.DPC_RNN(64, network='resnet18')
     with pytest.raises(RuntimeError):
         m(torch.randn(1, 8, 3, 5, 64, 64))                          # CPU tensor: loud failure, no fallback
+
+
+def test_dataparallel_two_replicas_match_oracle_per_shard():
+    """the reference's own multi-GPU wrapper (dpc/main.py:65): nn.DataParallel over OUR module -- thread per
+    GPU, replicated parameters, gathered [B,P,SQ,B2,P,SQ] score (B2 = B / n_gpu), rebuilt mask per replica."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip('needs 2 GPUs')
+    from oracle import dpc_oracle as O
+    fx = load_fixture('r18_img64_b2')
+    sd = O.synthetic_state_dict(fx['network'], fx['seed_w'])
+    m = build(fx['network'], fx['img'], fx['pred_step'], sd).eval()
+    dp = torch.nn.DataParallel(m, device_ids=[0, 1])
+    g = torch.Generator().manual_seed(77)
+    block = torch.randn(4, 8, 3, 5, 64, 64, generator=g)
+    score, mask = dp(block.cuda(0))
+    assert score.shape == (4, 3, 4, 2, 3, 4) and mask.shape == score.shape and mask.dtype == torch.int8
+    for r in range(2):                                   # each replica scores its own shard only (main.py:180,212)
+        ref_score, ref_mask = O.dpc_forward(block[2 * r:2 * r + 2], sd, fx['network'], 3)
+        e, l2 = rel_err(score[2 * r:2 * r + 2].cpu(), ref_score)
+        assert e < TOL and l2 < TOL, (r, e, l2)
+        assert torch.equal(mask[2 * r:2 * r + 2].cpu(), ref_mask)
+    # unchanged driver lines main.py:213-217 on the gathered tensors
+    B, P, SQ, B2 = score.shape[:4]
+    target = (mask == 1).view(B * P * SQ, B2 * P * SQ).to(int).argmax(1)
+    loss = torch.nn.functional.cross_entropy(score.view(B * P * SQ, B2 * P * SQ), target)
+    import dpc_b200
+    loss2 = dpc_b200.NCECriterion()(score.view(B * P * SQ, B2 * P * SQ), target)
+    assert abs(float(loss) - float(loss2)) < 1e-5 * max(1.0, abs(float(loss)))
+    loss.backward()
+    assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in m.parameters())
