@@ -362,12 +362,37 @@ def _wgrad_async(site, x_op, dy_op, main, side):
     return dw
 
 
+_CHAIN_STREAMS = {}
+
+
+def _chain_stream(device):
+    """high-priority stream for the dgrad -> BN-backward critical chain (the wgrad side stream is low priority,
+    so its CTAs only fill SMs the chain leaves idle, e.g. under the HBM-bound BN passes)"""
+    s = _CHAIN_STREAMS.get(device)
+    if s is None:
+        s = _CHAIN_STREAMS[device] = torch.cuda.Stream(device=device, priority=-1)
+    return s
+
+
 def backbone_backward(ctx, dout, P):
     """dout: rows [NB*To*Ho*Wo, 256].  Returns dict name -> grad (parameter layouts)."""
+    if not (OVERLAP_WGRAD and _TIMER is None):
+        return _backbone_backward(ctx, dout, P, None)
+    caller = torch.cuda.current_stream()
+    chain = _chain_stream(dout.device)
+    side = _side_stream(dout.device)
+    chain.wait_stream(caller)
+    with torch.cuda.stream(chain):
+        G = _backbone_backward(ctx, dout, P, side)
+    dout.record_stream(chain)
+    caller.wait_stream(chain)
+    return G
+
+
+def _backbone_backward(ctx, dout, P, side):
     L = lib()
     st = _stream()
     main = torch.cuda.current_stream()
-    side = _side_stream(dout.device) if (OVERLAP_WGRAD and _TIMER is None) else None
     G = {}
     for rec in reversed(ctx['blocks']):
         b = rec['spec']
