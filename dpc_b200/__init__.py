@@ -9,5 +9,6 @@ from .select_backbone import select_resnet           # noqa: F401
 from .model_3d import DPC_RNN                        # noqa: F401
 from .criterion import NCECriterion                  # noqa: F401
 from .parallel import FlatTrainer, shard_batch       # noqa: F401
+from .model_3d_lc import LC                          # noqa: F401
 
-__all__ = ['DPC_RNN', 'select_resnet', 'NCECriterion', 'FlatTrainer', 'shard_batch', 'lib', 'DpcLibError']
+__all__ = ['DPC_RNN', 'LC', 'select_resnet', 'NCECriterion', 'FlatTrainer', 'shard_batch', 'lib', 'DpcLibError']

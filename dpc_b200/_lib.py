@@ -60,6 +60,12 @@ _SIGS = {
     'dpc_nce_mask_fill': (c_int, [P, c_int, c_int, c_int, P]),
     'dpc_nce_ce_fwd': (c_int, [P, c_int, c_int, P, P, P]),
     'dpc_nce_ce_bwd': (c_int, [P, P, P, P, c_int, c_int, P]),
+    'dpc_bn_running_update': (c_int, [P, P, c_int64, c_float, c_float, P, P, c_int, P]),
+    'dpc_bn_rstd_from_var': (c_int, [P, c_float, P, c_int, P]),
+    'dpc_relu_pool_fwd': (c_int, [P, P, c_int, c_int, c_int64, P]),
+    'dpc_relu_pool_bwd': (c_int, [P, P, P, c_int, c_int, c_int64, P]),
+    'dpc_dropout_fwd': (c_int, [P, P, P, c_float, c_uint64, c_uint64, c_int64, P]),
+    'dpc_mul': (c_int, [P, P, P, c_int64, P]),
     'dpc_adam_step': (c_int, [P, P, P, P, c_int64, c_float, c_float, c_float, c_float, c_float, c_int, c_float, P]),
 }
 

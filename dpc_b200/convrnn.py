@@ -45,5 +45,52 @@ class ConvGRU(nn.Module):
         return float(self.dropout_layer.p)
 
     def forward(self, x, hidden_state=None):
-        raise NotImplementedError('stand-alone ConvGRU.forward (eval/LC) is a SURVEY.md §8(f) "next" row; '
-                                  'DPC_RNN.forward runs the fused CUDA GRU')
+        """x [B,T,C,H,W] -> (layer_output [B,T,C,H,W], last_state [B,1,C,H,W])  (convrnn.py:62-88).
+        Built for the configuration the reference uses: kernel_size 1, one layer, input == hidden == 256."""
+        from . import engine
+        if self.kernel_size != 1 or self.num_layers != 1 or self.input_size != self.hidden_size \
+                or self.hidden_size != engine.FEATURE_SIZE:
+            raise NotImplementedError('ConvGRU CUDA path: kernel_size=1, num_layers=1, input=hidden=%d only' % engine.FEATURE_SIZE)
+        if not x.is_cuda:
+            raise RuntimeError('dpc_b200 has no CPU path: input must be a CUDA tensor')
+        B, T, C, H, W = x.shape
+        h0 = None
+        if hidden_state is not None and hidden_state[0] is not None:
+            h0 = hidden_state[0].permute(0, 2, 3, 1).reshape(B * H * W, C).contiguous()
+        rows = x.permute(1, 0, 3, 4, 2).reshape(T * B * H * W, C).contiguous().float()
+        cell = self.cell_list[0]
+        params = [cell.reset_gate.weight, cell.reset_gate.bias, cell.update_gate.weight, cell.update_gate.bias,
+                  cell.out_gate.weight, cell.out_gate.bias]
+        p = float(self.dropout_layer.p) if self.training else 0.0
+        seed = (torch.initial_seed() * 0x9E3779B1 + next(_seq_calls) * 1000003) & 0x7FFFFFFFFFFFFFFF
+        need = torch.is_grad_enabled() and (x.requires_grad or any(q.requires_grad for q in params))
+        H_all = _GruSeqFn.apply(rows, h0, B * H * W, T, p, seed, need, *[q.contiguous() for q in params])
+        out = H_all.view(T, B, H, W, C).permute(1, 0, 4, 2, 3)
+        return out, out[:, -1:].contiguous()
+
+
+import itertools
+from torch.autograd.function import once_differentiable
+
+_seq_calls = itertools.count()
+
+
+class _GruSeqFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, rows, h0, R, T, p, seed, need, *params):
+        from . import engine
+        P = dict(zip(engine.HEAD_PARAM_NAMES[:6], params))
+        H_all, steps = engine.gru_sequence_forward(rows, h0, P, R, T, p, seed)
+        ctx.steps, ctx.rows, ctx.R, ctx.T, ctx.has_h0 = (steps if need else None), rows, R, T, h0 is not None
+        ctx.save_for_backward(*params)
+        return H_all
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dH_all):
+        from . import engine
+        P = dict(zip(engine.HEAD_PARAM_NAMES[:6], ctx.saved_tensors))
+        G = engine._new_head_grads(P, dH_all.device)
+        dX, dh0 = engine.gru_sequence_backward(ctx.steps, ctx.rows, dH_all.contiguous(), None, P, ctx.R, ctx.T, G)
+        ctx.steps = None
+        return (dX, dh0 if ctx.has_h0 else None, None, None, None, None, None) + tuple(G[n] for n in engine.HEAD_PARAM_NAMES[:6])

@@ -195,3 +195,108 @@ extern "C" int dpc_adam_step(float* p, const float* g, float* m, float* v, int64
     DPC_LAUNCH_CHECK();
     return DPC_OK;
 }
+
+// ---- pieces used by the LC classifier (eval/model_3d_lc.py): running BatchNorm statistics, ReLU-then-average
+// pooling, stand-alone dropout -----------------------------------------------------------------------------
+namespace {
+
+__global__ void bn_running_update_kernel(const float* __restrict__ mean, const float* __restrict__ rstd, double n,
+                                         float eps, float momentum, float* __restrict__ rm, float* __restrict__ rv, int C) {
+    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    const double r = (double)rstd[c];
+    double var_b = 1.0 / (r * r) - (double)eps;             // biased batch variance
+    if (var_b < 0.0) var_b = 0.0;
+    const double var_u = n > 1.0 ? var_b * n / (n - 1.0) : var_b;
+    rm[c] = (1.f - momentum) * rm[c] + momentum * mean[c];
+    rv[c] = (1.f - momentum) * rv[c] + momentum * (float)var_u;
+}
+
+__global__ void rstd_from_var_kernel(const float* __restrict__ var, float eps, float* __restrict__ rstd, int C) {
+    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c < C) rstd[c] = (float)(1.0 / sqrt((double)var[c] + (double)eps));
+}
+
+// feat[n, e] = mean_t relu(z[n, t, e])
+__global__ void relu_pool_fwd_kernel(const float4* __restrict__ z, float4* __restrict__ feat, long long NB, int T, long long E4) {
+    const float inv = 1.f / (float)T;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < NB * E4; i += (long long)gridDim.x * blockDim.x) {
+        const long long n = i / E4, e = i % E4;
+        float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int t = 0; t < T; ++t) {
+            const float4 v = z[(n * T + t) * E4 + e];
+            s.x += fmaxf(v.x, 0.f); s.y += fmaxf(v.y, 0.f); s.z += fmaxf(v.z, 0.f); s.w += fmaxf(v.w, 0.f);
+        }
+        feat[i] = make_float4(s.x * inv, s.y * inv, s.z * inv, s.w * inv);
+    }
+}
+__global__ void relu_pool_bwd_kernel(const float4* __restrict__ z, const float4* __restrict__ dfeat, float4* __restrict__ dz,
+                                     long long NB, int T, long long E4) {
+    const float inv = 1.f / (float)T;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < NB * E4; i += (long long)gridDim.x * blockDim.x) {
+        const long long n = i / E4, e = i % E4;
+        const float4 d = dfeat[i];
+        for (int t = 0; t < T; ++t) {
+            const float4 v = z[(n * T + t) * E4 + e];
+            dz[(n * T + t) * E4 + e] = make_float4(v.x > 0.f ? d.x * inv : 0.f, v.y > 0.f ? d.y * inv : 0.f,
+                                                   v.z > 0.f ? d.z * inv : 0.f, v.w > 0.f ? d.w * inv : 0.f);
+        }
+    }
+}
+
+__global__ void dropout_kernel(const float* __restrict__ x, float* __restrict__ y, float* __restrict__ keep, float p,
+                               uint64_t seed, uint64_t offset, long long n) {
+    const float scale = 1.f / (1.f - p);
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const float k = uniform01(seed, offset + (uint64_t)i) >= p ? scale : 0.f;
+        keep[i] = k;
+        y[i] = x[i] * k;
+    }
+}
+__global__ void mul_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ out, long long n) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        out[i] = a[i] * b[i];
+}
+
+}  // namespace
+
+extern "C" int dpc_bn_running_update(const float* mean, const float* rstd, int64_t rows, float eps, float momentum,
+                                     float* running_mean, float* running_var, int C, void* stream) {
+    DPC_REQUIRE(mean && rstd && running_mean && running_var && rows > 0 && C > 0, "dpc_bn_running_update: bad args");
+    bn_running_update_kernel<<<ceil_div(C, 128), 128, 0, as_stream(stream)>>>(mean, rstd, (double)rows, eps, momentum,
+                                                                             running_mean, running_var, C);
+    DPC_LAUNCH_CHECK();
+    return DPC_OK;
+}
+extern "C" int dpc_bn_rstd_from_var(const float* var, float eps, float* rstd, int C, void* stream) {
+    DPC_REQUIRE(var && rstd && C > 0, "dpc_bn_rstd_from_var: bad args");
+    rstd_from_var_kernel<<<ceil_div(C, 128), 128, 0, as_stream(stream)>>>(var, eps, rstd, C);
+    DPC_LAUNCH_CHECK();
+    return DPC_OK;
+}
+extern "C" int dpc_relu_pool_fwd(const float* z, float* feat, int NB, int T, int64_t E, void* stream) {
+    DPC_REQUIRE(z && feat && NB > 0 && T > 0 && E > 0 && E % 4 == 0, "dpc_relu_pool_fwd: bad args");
+    relu_pool_fwd_kernel<<<ew_grid((long long)NB * E / 4), 256, 0, as_stream(stream)>>>((const float4*)z, (float4*)feat, NB, T, E / 4);
+    DPC_LAUNCH_CHECK();
+    return DPC_OK;
+}
+extern "C" int dpc_relu_pool_bwd(const float* z, const float* dfeat, float* dz, int NB, int T, int64_t E, void* stream) {
+    DPC_REQUIRE(z && dfeat && dz && NB > 0 && T > 0 && E > 0 && E % 4 == 0, "dpc_relu_pool_bwd: bad args");
+    relu_pool_bwd_kernel<<<ew_grid((long long)NB * E / 4), 256, 0, as_stream(stream)>>>((const float4*)z, (const float4*)dfeat,
+                                                                                        (float4*)dz, NB, T, E / 4);
+    DPC_LAUNCH_CHECK();
+    return DPC_OK;
+}
+extern "C" int dpc_dropout_fwd(const float* x, float* y, float* keep, float p, uint64_t seed, uint64_t offset, int64_t n,
+                               void* stream) {
+    DPC_REQUIRE(x && y && keep && n > 0 && p >= 0.f && p < 1.f, "dpc_dropout_fwd: bad args");
+    dropout_kernel<<<ew_grid(n), 256, 0, as_stream(stream)>>>(x, y, keep, p, seed, offset, n);
+    DPC_LAUNCH_CHECK();
+    return DPC_OK;
+}
+extern "C" int dpc_mul(const float* a, const float* b, float* out, int64_t n, void* stream) {
+    DPC_REQUIRE(a && b && out && n > 0, "dpc_mul: bad args");
+    mul_kernel<<<ew_grid(n), 256, 0, as_stream(stream)>>>(a, b, out, n);
+    DPC_LAUNCH_CHECK();
+    return DPC_OK;
+}

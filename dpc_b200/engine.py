@@ -262,11 +262,35 @@ def backbone_param_names(network):
     return names
 
 
-def backbone_forward(network, x, P, need_ctx=True):
+BN_MOMENTUM = 0.1
+
+
+def _conv_bn(site, op, name, bn_state, training, st):
+    """conv + the BatchNorm statistics to normalise with: batch statistics (and, with running buffers in train
+    mode, their momentum update) or the running buffers (eval mode of track_running_stats=True)."""
+    L = lib()
+    if bn_state is not None and not training:
+        y = site.fwd(op, st)
+        rm, rv = bn_state[name]
+        rstd = torch.empty_like(rm)
+        L.bn_rstd_from_var(ptr(rv), BN_EPS, ptr(rstd), rm.numel(), st)
+        return y, rm, rstd
+    y, m, r = site.fwd_bn(op, st)
+    if bn_state is not None:
+        rm, rv = bn_state[name]
+        L.bn_running_update(ptr(m), ptr(r), site.rows_out, BN_EPS, BN_MOMENTUM, ptr(rm), ptr(rv), rm.numel(), st)
+    return y, m, r
+
+
+def backbone_forward(network, x, P, need_ctx=True, bn_state=None, training=True):
     """x [NB,3,T,H,W] fp32 contiguous CUDA; P: name -> tensor.  Returns (feature rows [NB*To*Ho*Wo, 256],
-    (To,Ho,Wo), ctx)."""
+    (To,Ho,Wo), ctx).  bn_state: None (track_running_stats=False: batch statistics always) or
+    {bn name: (running_mean, running_var)} (track_running_stats=True, eval/model_3d_lc.py:26)."""
     L = lib()
     st = _stream()
+    running = bn_state is not None and not training
+    if running and need_ctx:
+        raise NotImplementedError('backward through eval-mode (running-statistics) BatchNorm is not built')
     NB, Cin, T, H, W = x.shape
     if Cin != 3:
         raise ValueError('backbone expects 3 input channels, got %d' % Cin)
@@ -274,13 +298,21 @@ def backbone_forward(network, x, P, need_ctx=True):
     rows0 = NB * T * Ho * Wo
     y0 = _empty((rows0, 64), x)
     if USE_TC:
-        ws0 = torch.empty(128, dtype=torch.float64, device=x.device)
-        m0, r0 = _empty((64,), x), _empty((64,), x)
+        ws0 = None if running else torch.empty(128, dtype=torch.float64, device=x.device)
         _timed('stem_fwd')(L.stem_conv_fwd_tc)(ptr(x), ptr(P['conv1.weight']), ptr(y0), ptr(ws0), NB, T, H, W, st)
-        L.bn_finalize(ptr(ws0), rows0, 64, BN_EPS, ptr(m0), ptr(r0), st)
+        if not running:
+            m0, r0 = _empty((64,), x), _empty((64,), x)
+            L.bn_finalize(ptr(ws0), rows0, 64, BN_EPS, ptr(m0), ptr(r0), st)
     else:
         _timed('stem_fwd')(L.stem_conv_fwd)(ptr(x), ptr(P['conv1.weight']), ptr(y0), NB, T, H, W, st)
-        m0, r0 = _bn_stats(y0, rows0, 64, st)
+        if not running:
+            m0, r0 = _bn_stats(y0, rows0, 64, st)
+    if running:
+        m0 = bn_state['bn1'][0]
+        r0 = torch.empty_like(m0)
+        L.bn_rstd_from_var(ptr(bn_state['bn1'][1]), BN_EPS, ptr(r0), 64, st)
+    elif bn_state is not None:
+        L.bn_running_update(ptr(m0), ptr(r0), rows0, BN_EPS, BN_MOMENTUM, ptr(bn_state['bn1'][0]), ptr(bn_state['bn1'][1]), 64, st)
     Hp, Wp = _out_extent(Ho, 3, 2, 1), _out_extent(Wo, 3, 2, 1)
     a0 = _empty((NB * T * Hp * Wp, 64), x)
     _timed('stem_pool_fwd')(L.bn_relu_maxpool_fwd)(ptr(y0), ptr(m0), ptr(r0), ptr(P['bn1.weight']), ptr(P['bn1.bias']), ptr(a0),
@@ -303,14 +335,14 @@ def backbone_forward(network, x, P, need_ctx=True):
             s1 = (1, b['stride'], b['stride'])
         c1 = Site(NB, dims, b['inplanes'], b['planes'], k, s1, pad)
         c1.pack(P[p + '.conv1.weight'], st)
-        y1, m1, r1 = c1.fwd_bn(cur_op, st)
+        y1, m1, r1 = _conv_bn(c1, cur_op, p + '.bn1', bn_state, training, st)
         # tensor-core path: the normalise pass writes the next conv's operand planes directly
         a1, a1_pl = _bn_apply(y1, m1, r1, P[p + '.bn1.weight'], P[p + '.bn1.bias'], True, c1.rows_out, c1.Co, st,
                               want_rows=not tc, want_planes=tc)
         a1_op = a1_pl if tc else a1
         c2 = Site(NB, c1.dims_out, b['planes'], b['planes'], k, (1, 1, 1), pad)
         c2.pack(P[p + '.conv2.weight'], st)
-        y2, m2, r2 = c2.fwd_bn(a1_op, st)
+        y2, m2, r2 = _conv_bn(c2, a1_op, p + '.bn2', bn_state, training, st)
         rec = dict(spec=b, c1=c1, c2=c2, xin_op=cur_op, y1=y1, m1=m1, r1=r1, a1=a1, a1_op=a1_op,
                    y2=y2, m2=m2, r2=r2, tc=tc)
         want_rows = (not tc) or last                 # the last block's output feeds the head as fp32 rows
@@ -318,7 +350,7 @@ def backbone_forward(network, x, P, need_ctx=True):
         if b['downsample']:
             cd = Site(NB, dims, b['inplanes'], b['planes'], (1, 1, 1), s1, (0, 0, 0))
             cd.pack(P[p + '.downsample.0.weight'], st)
-            yd, md, rd = cd.fwd_bn(cur_op, st)
+            yd, md, rd = _conv_bn(cd, cur_op, p + '.downsample.1', bn_state, training, st)
             out, out_pl = _bn_apply(y2, m2, r2, P[p + '.bn2.weight'], P[p + '.bn2.bias'], b['final_relu'],
                                     c2.rows_out, c2.Co, st, res=yd,
                                     rbn=(md, rd, P[p + '.downsample.1.weight'], P[p + '.downsample.1.bias']),
@@ -672,6 +704,142 @@ def head_backward(ctx, dscore, P):
         L.scatter_rows(ptr(dx), ptr(dfeat), R, D, S, N * S, t * S, 0, st)
     dz4 = _empty((NB * To * S, D), dscore)
     L.pool_split_bwd(ptr(ctx['finf_all']), ptr(dfinf_all), ptr(dfeat), ptr(dz4), NB, To, S, D, st)
+    del G['_bzr']
+    return dz4, G
+
+
+# ==================================================================================================
+# general ConvGRU sequence (kernel_size 1, one layer) and the LC classifier head
+#   ConvGRU.forward         /root/reference/backbone/convrnn.py:62-88
+#   LC.forward (after the backbone)   /root/reference/eval/model_3d_lc.py:53-65
+# ==================================================================================================
+def gru_sequence_forward(X_all, h0, P, R, T, dropout_p, seed):
+    """X_all rows [T*R, D] (step-major); h0 [R, D] or None.  Returns (H_all [T*R, D] post-dropout states, steps)."""
+    st = _stream()
+    D = FEATURE_SIZE
+    gru = _Gru(P, D, st)
+    XP = gru.xproj(X_all, T * R)
+    h = h0 if h0 is not None else torch.zeros((R, D), dtype=torch.float32, device=X_all.device)
+    H_all = _empty((T * R, D), X_all)
+    steps = []
+    for t in range(T):
+        h, sv = gru.step(XP, t * R, h, R, dropout_p, seed, t * R * D)
+        H_all[t * R:(t + 1) * R].copy_(h)
+        steps.append(sv)
+    return H_all, steps
+
+
+def gru_sequence_backward(steps, X_all, dH_all, dh_last, P, R, T, G):
+    """dH_all [T*R, D] or None: gradient w.r.t. every step's output; dh_last [R, D] or None: extra gradient on the
+    final state.  Accumulates weight grads into G.  Returns (dX_all [T*R, D], dh0)."""
+    st = _stream()
+    D = FEATURE_SIZE
+    gru = _Gru(P, D, st)
+    L = lib()
+    dX_all = _empty((T * R, D), X_all)
+    dh = None
+    if dh_last is not None:
+        dh = torch.empty_like(dh_last)
+        dh.copy_(dh_last)
+    for t in reversed(range(T)):
+        if dH_all is not None:
+            cur_ptr = dH_all.data_ptr() + t * R * D * 4
+            if dh is None:
+                dh = _empty((R, D), X_all)
+                L.gather_rows(cur_ptr, ptr(dh), R, D, R, R, 0, st)
+            else:
+                L.scatter_rows(cur_ptr, ptr(dh), R, D, R, R, 0, 1, st)           # dh += dH_all[t]
+        if dh is None:
+            dh = torch.zeros((R, D), dtype=torch.float32, device=X_all.device)
+        dx, dh = gru.step_bwd(steps[t], X_all[t * R:(t + 1) * R], dh, R, G)
+        dX_all[t * R:(t + 1) * R].copy_(dx)
+    return dX_all, dh
+
+
+def _new_head_grads(P, dev):
+    D = FEATURE_SIZE
+    G = {n: torch.zeros_like(P[n]) for n in HEAD_PARAM_NAMES[:6]}
+    G['_bzr'] = torch.zeros(2 * D, dtype=torch.float32, device=dev)
+    G['agg.cell_list.0.update_gate.bias'] = G['_bzr'][:D]
+    G['agg.cell_list.0.reset_gate.bias'] = G['_bzr'][D:]
+    return G
+
+
+LC_PARAM_NAMES = HEAD_PARAM_NAMES[:6] + ['final_bn.weight', 'final_bn.bias', 'final_fc.1.weight', 'final_fc.1.bias']
+
+
+def lc_head_forward(z4, dims, B, N, P, final_bn_state, training, gru_p, fc_p, seed, need_ctx=True):
+    """z4: backbone rows [B*N*To*S, D].  Returns (output [B, num_class], context [B, D], ctx)."""
+    L = lib()
+    st = _stream()
+    To, Lh, Lw = dims
+    S, D = Lh * Lw, FEATURE_SIZE
+    NB, R = B * N, B * S
+    feat = _empty((NB * S, D), z4)
+    L.relu_pool_fwd(ptr(z4), ptr(feat), NB, To, S * D, st)                   # ReLU, then temporal mean
+    X_all = _empty((N * R, D), z4)
+    for t in range(N):
+        L.gather_rows(ptr(feat), X_all.data_ptr() + t * R * D * 4, R, D, S, N * S, t * S, st)
+    H_all, steps = gru_sequence_forward(X_all, None, P, R, N, gru_p if training else 0.0, seed)
+    h_last = H_all[(N - 1) * R:]
+    vec = _empty((B, D), z4)
+    dummy = _empty((B, D), z4)
+    L.pool_split_fwd(ptr(h_last), ptr(vec), ptr(dummy), B, S, 1, D, st)       # spatial mean over the S positions
+    if training:
+        mean, rstd = _bn_stats(vec, B, D, st)
+        L.bn_running_update(ptr(mean), ptr(rstd), B, BN_EPS, BN_MOMENTUM, ptr(final_bn_state[0]), ptr(final_bn_state[1]), D, st)
+    else:
+        mean = final_bn_state[0]
+        rstd = torch.empty_like(mean)
+        L.bn_rstd_from_var(ptr(final_bn_state[1]), BN_EPS, ptr(rstd), D, st)
+    context, _ = _bn_apply(vec, mean, rstd, P['final_bn.weight'], P['final_bn.bias'], False, B, D, st)
+    keep = None
+    cin = context
+    if training and fc_p > 0:
+        cin, keep = torch.empty_like(context), torch.empty_like(context)
+        L.dropout_fwd(ptr(context), ptr(cin), ptr(keep), float(fc_p), seed ^ 0x5DEECE66D, 0, B * D, st)
+    W, bias = P['final_fc.1.weight'], P['final_fc.1.bias']
+    nc = W.shape[0]
+    out = _empty((B, nc), z4)
+    _gemm(0, 1, B, nc, D, cin, D, W, D, out, nc, st)
+    L.bias_relu(ptr(out), ptr(bias), ptr(out), 0, B, nc, st)
+    ctx = None
+    if need_ctx:
+        if not training:
+            raise NotImplementedError('backward through eval-mode (running-statistics) BatchNorm is not built')
+        ctx = dict(B=B, N=N, S=S, D=D, To=To, R=R, z4=z4, X_all=X_all, steps=steps, vec=vec, mean=mean, rstd=rstd,
+                   keep=keep, cin=cin, nc=nc)
+    return out, context, ctx
+
+
+def lc_head_backward(ctx, dout, dcontext, P):
+    L = lib()
+    st = _stream()
+    B, N, S, D, To, R, nc = (ctx[k] for k in ('B', 'N', 'S', 'D', 'To', 'R', 'nc'))
+    NB = B * N
+    dev = dout.device
+    G = _new_head_grads(P, dev)
+    W = P['final_fc.1.weight']
+    G['final_fc.1.weight'] = _empty((nc, D), dout)
+    _gemm(1, 0, nc, D, B, dout, nc, ctx['cin'], D, G['final_fc.1.weight'], D, st)
+    G['final_fc.1.bias'] = _empty((nc,), dout)
+    L.colsum(ptr(dout), B, nc, ptr(G['final_fc.1.bias']), 0, st)
+    dc = _empty((B, D), dout)
+    _gemm(0, 0, B, D, nc, dout, nc, W, D, dc, D, st)
+    if ctx['keep'] is not None:
+        L.mul(ptr(dc), ptr(ctx['keep']), ptr(dc), B * D, st)
+    if dcontext is not None:
+        L.scatter_rows(ptr(dcontext.contiguous()), ptr(dc), B, D, B, B, 0, 1, st)      # dc += dcontext
+    dvec, _, G['final_bn.weight'], G['final_bn.bias'], _ = _bn_bwd(dc, None, False, ctx['vec'], ctx['mean'], ctx['rstd'],
+                                                                 P['final_bn.weight'], B, D, st)
+    dh_last = _empty((R, D), dout)
+    L.pool_split_bwd(ptr(ctx['vec']), ptr(dvec), None, ptr(dh_last), B, S, 1, D, st)
+    dX_all, _ = gru_sequence_backward(ctx['steps'], ctx['X_all'], None, dh_last, P, R, N, G)
+    dfeat = _empty((NB * S, D), dout)
+    for t in range(N):
+        L.scatter_rows(dX_all.data_ptr() + t * R * D * 4, ptr(dfeat), R, D, S, N * S, t * S, 0, st)
+    dz4 = torch.empty_like(ctx['z4'])
+    L.relu_pool_bwd(ptr(ctx['z4']), ptr(dfeat), ptr(dz4), NB, To, S * D, st)
     del G['_bzr']
     return dz4, G
 

@@ -191,6 +191,20 @@ int dpc_nce_ce_fwd(const float* score, int rows, int M, float* lse, float* out, 
 int dpc_nce_ce_bwd(const float* score, const float* lse, const float* gscale, float* dscore,
                    int rows, int M, void* stream);
 
+/* ---- LC classifier pieces (eval/model_3d_lc.py:12-65) ------------------------
+ * BatchNorm with running statistics (track_running_stats=True): train mode normalises with batch statistics
+ * and updates the buffers (momentum, unbiased variance); eval mode normalises with the buffers. */
+int dpc_bn_running_update(const float* mean, const float* rstd, int64_t rows, float eps, float momentum,
+                          float* running_mean, float* running_var, int C, void* stream);
+int dpc_bn_rstd_from_var(const float* var, float eps, float* rstd, int C, void* stream);
+/* feat[n,e] = mean_t relu(z[n,t,e])  (LC applies ReLU BEFORE the temporal average, model_3d_lc.py:53-55) */
+int dpc_relu_pool_fwd(const float* z, float* feat, int NB, int T, int64_t E, void* stream);
+int dpc_relu_pool_bwd(const float* z, const float* dfeat, float* dz, int NB, int T, int64_t E, void* stream);
+/* y = x * keep, keep in {0, 1/(1-p)} (nn.Dropout before the final Linear, model_3d_lc.py:43) */
+int dpc_dropout_fwd(const float* x, float* y, float* keep, float p, uint64_t seed, uint64_t offset, int64_t n,
+                    void* stream);
+int dpc_mul(const float* a, const float* b, float* out, int64_t n, void* stream);
+
 /* ---- optimiser ------------------------------------------------------------------------------
  * torch.optim.Adam(lr, weight_decay) (L2, not AdamW), dpc/main.py:81,231, over a flat buffer. */
 int dpc_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1,

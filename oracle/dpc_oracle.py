@@ -381,3 +381,107 @@ def cpu_train_step_time(network='resnet18', img=128, batch=4, steps=3, warmup=1,
             times.append(dt)
     times.sort()
     return times[len(times) // 2]
+
+
+# --------------------------------------------------------------------------------------------
+# LC classifier: restatement of /root/reference/eval/model_3d_lc.py:47-65
+# --------------------------------------------------------------------------------------------
+def lc_param_shapes(network, num_class=101):
+    """parameters AND buffers of LC in state_dict order (track_running_stats=True everywhere)"""
+    sh = OrderedDict()
+
+    def bn(prefix, c):
+        sh[prefix + '.weight'] = (c,); sh[prefix + '.bias'] = (c,)
+        sh[prefix + '.running_mean'] = (c,); sh[prefix + '.running_var'] = (c,); sh[prefix + '.num_batches_tracked'] = ()
+    sh['backbone.conv1.weight'] = (64, 3, 1, 7, 7)
+    bn('backbone.bn1', 64)
+    for b in backbone_spec(network):
+        p = 'backbone.' + b['name']
+        k = (3, 3, 3) if b['is3d'] else (1, 3, 3)
+        sh[p + '.conv1.weight'] = (b['planes'], b['inplanes']) + k
+        bn(p + '.bn1', b['planes'])
+        sh[p + '.conv2.weight'] = (b['planes'], b['planes']) + k
+        bn(p + '.bn2', b['planes'])
+        if b['downsample']:
+            sh[p + '.downsample.0.weight'] = (b['planes'], b['inplanes'], 1, 1, 1)
+            bn(p + '.downsample.1', b['planes'])
+    D = FEATURE_SIZE
+    for cell in ('agg.ConvGRUCell_00', 'agg.cell_list.0'):
+        for g in ('reset_gate', 'update_gate', 'out_gate'):
+            sh['%s.%s.weight' % (cell, g)] = (D, 2 * D, 1, 1)
+            sh['%s.%s.bias' % (cell, g)] = (D,)
+    bn('final_bn', D)
+    sh['final_fc.1.weight'] = (num_class, D)
+    sh['final_fc.1.bias'] = (num_class,)
+    return sh
+
+
+def lc_synthetic_state_dict(network, seed, num_class=101):
+    g = torch.Generator().manual_seed(seed)
+    sd = OrderedDict()
+    for k, shape in lc_param_shapes(network, num_class).items():
+        if k.startswith('agg.cell_list.0'):
+            sd[k] = sd[k.replace('agg.cell_list.0', 'agg.ConvGRUCell_00')]
+            continue
+        leaf = k.rsplit('.', 1)[1]
+        if leaf == 'num_batches_tracked':
+            t = torch.tensor(3, dtype=torch.int64)
+        elif leaf == 'running_mean':
+            t = 0.2 * torch.randn(shape, generator=g)
+        elif leaf == 'running_var':
+            t = 0.5 + torch.rand(shape, generator=g)
+        elif len(shape) == 1 and leaf == 'weight':
+            t = 0.5 + torch.rand(shape, generator=g)
+        elif leaf == 'bias':
+            t = 0.1 * torch.randn(shape, generator=g)
+        elif k.startswith('backbone.'):
+            t = math.sqrt(2.0 / (shape[0] * shape[2] * shape[3] * shape[4])) * torch.randn(shape, generator=g)
+        else:
+            t = torch.randn(shape, generator=g) / math.sqrt(shape[1])
+        sd[k] = t
+    return sd
+
+
+def _bn_rs(x, sd, prefix, training, momentum=0.1, eps=1e-5, new_stats=None):
+    """nn.BatchNorm(track_running_stats=True): train -> batch statistics (+ records the updated buffers in
+    new_stats), eval -> running statistics"""
+    rm, rv = sd[prefix + '.running_mean'], sd[prefix + '.running_var']
+    if training:
+        rm2, rv2 = rm.clone(), rv.clone()
+        y = F.batch_norm(x, rm2, rv2, sd[prefix + '.weight'], sd[prefix + '.bias'], True, momentum, eps)
+        if new_stats is not None:
+            new_stats[prefix + '.running_mean'], new_stats[prefix + '.running_var'] = rm2, rv2
+        return y
+    return F.batch_norm(x, rm, rv, sd[prefix + '.weight'], sd[prefix + '.bias'], False, momentum, eps)
+
+
+def lc_forward(block, sd, network='resnet18', training=False, new_stats=None):
+    """LC.forward with dropout off (eval, or train with p = 0).  Returns (output [B,1,num_class], context [B,1,D])."""
+    B, N, C, SL, H, W = block.shape
+    D = FEATURE_SIZE
+    last_duration = int(math.ceil(SL / 4))
+    L = int(math.ceil(H / 32))
+    bn = lambda x, p: _bn_rs(x, sd, p, training, new_stats=new_stats)
+    x = block.reshape(B * N, C, SL, H, W)
+    x = F.conv3d(x, sd['backbone.conv1.weight'], None, (1, 2, 2), (0, 3, 3))
+    x = F.max_pool3d(F.relu(bn(x, 'backbone.bn1')), (1, 3, 3), (1, 2, 2), (0, 1, 1))
+    for b in backbone_spec(network):
+        p = 'backbone.' + b['name']
+        if b['is3d']:
+            s1, pad, sds = (b['stride'],) * 3, (1, 1, 1), (b['stride'],) * 3
+        else:
+            s1, pad, sds = (1, b['stride'], b['stride']), (0, 1, 1), (1, b['stride'], b['stride'])
+        out = F.relu(bn(F.conv3d(x, sd[p + '.conv1.weight'], None, s1, pad), p + '.bn1'))
+        out = bn(F.conv3d(out, sd[p + '.conv2.weight'], None, 1, pad), p + '.bn2')
+        res = bn(F.conv3d(x, sd[p + '.downsample.0.weight'], None, sds, 0), p + '.downsample.1') if b['downsample'] else x
+        out = out + res
+        x = F.relu(out) if b['final_relu'] else out
+    feat = F.relu(x)                                                 # model_3d_lc.py:53
+    feat = F.avg_pool3d(feat, (last_duration, 1, 1), stride=1).reshape(B, N, D, L, L)
+    h = torch.zeros(B, D, L, L, dtype=block.dtype)
+    for t in range(N):                                               # context, _ = self.agg(feature)
+        h = gru_cell(feat[:, t], h, sd)
+    context = h.mean((2, 3)).unsqueeze(1)                            # avg_pool3d over (1, L, L)   [B,1,D]
+    context = _bn_rs(context.transpose(-1, -2), sd, 'final_bn', training, new_stats=new_stats).transpose(-1, -2)
+    output = F.linear(context, sd['final_fc.1.weight'], sd['final_fc.1.bias']).view(B, -1, sd['final_fc.1.weight'].shape[0])
+    return output, context

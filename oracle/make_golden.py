@@ -136,5 +136,43 @@ def main():
     print('init checks saved')
 
 
-if __name__ == '__main__':
+if __name__ == '__main__' and '--lc' not in sys.argv:
     main()
+
+
+def make_lc(network='resnet18', img=64, B=3, seed_w=51, seed_x=52, num_class=101):
+    """golden vectors of the reference LC classifier (eval/model_3d_lc.py), eval and train (dropout p = 0) mode"""
+    sys.path.insert(0, os.path.join(REF, 'eval'))
+    with contextlib.redirect_stdout(io.StringIO()):
+        import model_3d_lc as ref_lc
+        m = ref_lc.LC(sample_size=img, num_seq=8, seq_len=5, network=network, dropout=0.0, num_class=num_class)
+    sd = O.lc_synthetic_state_dict(network, seed_w, num_class)
+    assert list(m.state_dict().keys()) == list(sd.keys()), 'LC state_dict key order differs'
+    m.load_state_dict(sd, strict=True)
+    m.agg.dropout_layer.p = 0.0
+    g = torch.Generator().manual_seed(seed_x)
+    block = torch.randn(B, 8, 3, 5, img, img, generator=g)
+    fx = dict(network=network, img=img, B=B, seed_w=seed_w, seed_x=seed_x, num_class=num_class, keys=list(sd.keys()))
+    m.eval()
+    with torch.no_grad():
+        out, ctxv = m(block)
+    fx['eval_output'], fx['eval_context'] = out.clone(), ctxv.clone()
+    m.train()
+    out, ctxv = m(block)
+    fx['train_output'], fx['train_context'] = out.detach().clone(), ctxv.detach().clone()
+    target = torch.arange(B) % num_class
+    loss = F.cross_entropy(out.view(B, num_class), target)
+    loss.backward()
+    fx['train_loss'] = float(loss.detach())
+    fx['grads'] = {k: sample(p.grad, 512) for k, p in m.named_parameters()}
+    new = m.state_dict()
+    fx['new_stats'] = {k: new[k].clone() for k in new if 'running' in k and ('final_bn' in k or 'bn1.' in k[:13] or 'layer4.1' in k)}
+    fx['num_batches_tracked'] = int(new['final_bn.num_batches_tracked'])
+    return fx
+
+
+if __name__ == '__main__' and '--lc' in sys.argv:
+    fx = make_lc()
+    path = os.path.join(ROOT, 'tests', 'golden', 'lc_r18_img64_b3.pt')
+    torch.save(fx, path)
+    print('lc fixture', fx['train_loss'], '%.1f KB' % (os.path.getsize(path) / 1e3))

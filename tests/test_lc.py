@@ -1,0 +1,90 @@
+"""LC classifier (/root/reference/eval/model_3d_lc.py): oracle vs the reference's golden
+vectors on CPU, and the B200 path vs both on the GPU."""
+import io
+import contextlib
+
+import pytest
+import torch
+
+from oracle import dpc_oracle as O
+from tests.util import load_fixture, rel_err, check_sample_l2
+
+
+def _block(fx):
+    g = torch.Generator().manual_seed(fx['seed_x'])
+    return torch.randn(fx['B'], 8, 3, 5, fx['img'], fx['img'], generator=g)
+
+
+def test_lc_oracle_matches_reference():
+    fx = load_fixture('lc_r18_img64_b3')
+    sd = O.lc_synthetic_state_dict(fx['network'], fx['seed_w'], fx['num_class'])
+    assert list(sd.keys()) == fx['keys']
+    block = _block(fx)
+    out, ctxv = O.lc_forward(block, sd, fx['network'], training=False)
+    assert rel_err(out, fx['eval_output'])[0] < 2e-5 and rel_err(ctxv, fx['eval_context'])[0] < 2e-5
+    new = {}
+    out, ctxv = O.lc_forward(block, sd, fx['network'], training=True, new_stats=new)
+    assert rel_err(out, fx['train_output'])[0] < 2e-5 and rel_err(ctxv, fx['train_context'])[0] < 2e-5
+    for k, v in fx['new_stats'].items():
+        assert rel_err(new[k], v)[0] < 2e-5, k
+
+
+@pytest.mark.gpu
+def test_lc_cuda_matches_reference_and_oracle():
+    from dpc_b200.model_3d_lc import LC
+    fx = load_fixture('lc_r18_img64_b3')
+    sd = O.lc_synthetic_state_dict(fx['network'], fx['seed_w'], fx['num_class'])
+    with contextlib.redirect_stdout(io.StringIO()):
+        m = LC(fx['img'], 8, 5, network=fx['network'], dropout=0.0, num_class=fx['num_class'])
+    assert list(m.state_dict().keys()) == fx['keys']
+    m.load_state_dict(sd, strict=True)
+    m.agg.dropout_layer.p = 0.0
+    m = m.cuda()
+    block = _block(fx).cuda()
+    m.eval()
+    with torch.no_grad():
+        out, ctxv = m(block)
+    assert out.shape == fx['eval_output'].shape and ctxv.shape == fx['eval_context'].shape
+    assert rel_err(out, fx['eval_output'])[0] < 1e-3 and rel_err(ctxv, fx['eval_context'])[0] < 1e-3
+    m.train()
+    out, ctxv = m(block)
+    assert rel_err(out, fx['train_output'])[0] < 1e-3 and rel_err(ctxv, fx['train_context'])[0] < 1e-3
+    B, nc = fx['B'], fx['num_class']
+    loss = torch.nn.functional.cross_entropy(out.view(B, nc), (torch.arange(B) % nc).cuda())
+    assert abs(float(loss) - fx['train_loss']) < 1e-3 * max(1.0, fx['train_loss'])
+    loss.backward()
+    new = m.state_dict()
+    for k, v in fx['new_stats'].items():                       # running statistics after one train-mode forward
+        assert rel_err(new[k], v)[0] < 1e-3, k
+    assert int(new['final_bn.num_batches_tracked']) == fx['num_batches_tracked']
+    for k, p in m.named_parameters():                          # gradients: chaotic at B = 3 (see test_parity_gpu.GRAD_TOL)
+        assert p.grad is not None, k
+        check_sample_l2(p.grad, fx['grads'][k], 6e-2, k)
+
+
+@pytest.mark.gpu
+def test_standalone_convgru_forward_backward():
+    """ConvGRU.forward (convrnn.py:62-88) with k = 1, one layer: all hidden states + last state, and BPTT"""
+    from dpc_b200.convrnn import ConvGRU
+    torch.manual_seed(3)
+    g = ConvGRU(256, 256, 1, 1).cuda().eval()
+    sd = {k: v.detach().cpu() for k, v in g.state_dict().items()}
+    x = torch.randn(2, 4, 256, 3, 3, device='cuda', requires_grad=True)
+    out, last = g(x)
+    assert out.shape == (2, 4, 256, 3, 3) and last.shape == (2, 1, 256, 3, 3)
+    xr = x.detach().cpu().requires_grad_(True)
+    h = torch.zeros(2, 256, 3, 3)
+    hs = []
+    sdo = {'agg.cell_list.0.' + k[len('cell_list.0.'):]: v for k, v in sd.items() if k.startswith('cell_list.0.')}
+    sdo = {k: v.clone().requires_grad_(True) for k, v in sdo.items()}
+    for t in range(4):
+        h = O.gru_cell(xr[:, t], h, sdo)
+        hs.append(h)
+    ref = torch.stack(hs, 1)
+    assert rel_err(out, ref)[0] < 1e-4 and rel_err(last[:, 0], ref[:, -1])[0] < 1e-4
+    w = torch.randn_like(ref)
+    (ref * w).sum().backward()
+    (out * w.cuda()).sum().backward()
+    assert rel_err(x.grad, xr.grad)[0] < 1e-3
+    assert rel_err(g.cell_list[0].out_gate.weight.grad, sdo['agg.cell_list.0.out_gate.weight'].grad)[0] < 1e-3
+    assert rel_err(g.cell_list[0].update_gate.bias.grad, sdo['agg.cell_list.0.update_gate.bias'].grad)[0] < 1e-3
