@@ -94,6 +94,10 @@ __device__ __forceinline__ uint32_t setup_common(const SmemPlan& sp, const uint8
 
 // One warp's share of a finished tile: TMEM lanes [32q, 32q+32) = tile rows; adds the two accumulators,
 // stores the fp32 rows, and (optionally) accumulates the BatchNorm partial sums of the tile.
+__device__ __forceinline__ void tile_epilogue_rows(const TcParams& p, float* __restrict__ y, int accumulate,
+                                                   float* stat_smem, uint32_t tmem_d, uint32_t tmem_c, int q, int lane,
+                                                   bool valid, long long row, int ncol0);
+
 __device__ __forceinline__ void tile_epilogue(const TcParams& p, float* __restrict__ y, int accumulate,
                                               float* stat_smem, uint32_t tmem_d, uint32_t tmem_c, int q, int lane,
                                               int n0, int t0, int h0, int w0, int ncol0) {
@@ -103,12 +107,20 @@ __device__ __forceinline__ void tile_epilogue(const TcParams& p, float* __restri
     const bool valid = r < p.box_rows && n < p.NB && t < p.To && h < p.Ho && w < p.Wo;
     const long long row = (long long)n * p.out_sn + (long long)t * p.out_st + (long long)h * p.out_sh +
                           (long long)w * p.out_sw + p.out_base;
-    float* yrow = y + row * p.Co + ncol0;
+    tile_epilogue_rows(p, y, accumulate, stat_smem, tmem_d, tmem_c, q, lane, valid, row, ncol0);
+}
+
+// `valid` / `row`: whether this lane's accumulator row is a real output position, and which one
+__device__ __forceinline__ void tile_epilogue_rows(const TcParams& p, float* __restrict__ y, int accumulate,
+                                                   float* stat_smem, uint32_t tmem_d, uint32_t tmem_c, int q, int lane,
+                                                   bool valid, long long row, int ncol0) {
+    float* yrow = y + (valid ? row : 0) * p.Co + ncol0;
     const bool vec = (p.Co & 3) == 0;
     for (int c0 = 0; c0 < p.BN; c0 += 32) {
         uint32_t v[32], u[32];
-        tmem_ld32(tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
-        tmem_ld32(tmem_c + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, u);
+        tmem_ld32_nowait(tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+        tmem_ld32_nowait(tmem_c + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, u);
+        tmem_ld_wait();
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(u[j]));
         if (valid) {
@@ -214,6 +226,10 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p, float* __r
         if (elect_one()) {
             // instruction descriptor: D=f32, A=B=bf16, both K-major, N = BN, M = 128
             const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.BN >> 3) << 17) | ((128u >> 4) << 24);
+            // the B_hi and B_lo tiles are adjacent in a stage and so are the two accumulators: for BN <= 128 they
+            // are one N = 2*BN operand / destination
+            const bool wide = p.BN <= 128 && p.BN >= 16;
+            const uint32_t idesc2 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)((2 * p.BN) >> 3) << 17) | ((128u >> 4) << 24);
             int s = 0; uint32_t ph = 0;
             for (int kb = 0; kb < num_kb; ++kb) {
                 mbar_wait(sp.full(s), ph);
@@ -225,8 +241,12 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p, float* __r
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {               // 4 x UMMA_K(16) = 64 channels; +32 B per step
                     const uint64_t ko = (uint64_t)(k * 2);
-                    umma_bf16(tmem_d, ahi + ko, bhi + ko, idesc, (kb | k) ? 1u : 0u);
-                    umma_bf16(tmem_c, ahi + ko, blo + ko, idesc, (kb | k) ? 1u : 0u);
+                    if (wide) {                              // A_hi x [B_hi ; B_lo]: one instruction, both accumulators
+                        umma_bf16(tmem_d, ahi + ko, bhi + ko, idesc2, (kb | k) ? 1u : 0u);
+                    } else {
+                        umma_bf16(tmem_d, ahi + ko, bhi + ko, idesc, (kb | k) ? 1u : 0u);
+                        umma_bf16(tmem_c, ahi + ko, blo + ko, idesc, (kb | k) ? 1u : 0u);
+                    }
                     umma_bf16(tmem_c, alo + ko, bhi + ko, idesc, 1u);
                 }
                 umma_commit(sp.empty(s));                   // frees the smem stage when these MMAs retire
@@ -355,6 +375,7 @@ conv_tc_persist_kernel(const __grid_constant__ TcMaps maps, const TcParams p, fl
     } else if (warp == 1) {
         if (elect_one()) {
             const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.BN >> 3) << 17) | ((128u >> 4) << 24);
+            const uint32_t idesc2 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)((2 * p.BN) >> 3) << 17) | ((128u >> 4) << 24);
             if (resident_b && my_tiles > 0) mbar_wait(w_full, 0);
             int s = 0; uint32_t ph = 0;
             for (int i = 0; i < my_tiles; ++i) {
@@ -372,8 +393,7 @@ conv_tc_persist_kernel(const __grid_constant__ TcMaps maps, const TcParams p, fl
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
                         const uint64_t ko = (uint64_t)(k * 2);
-                        umma_bf16(td, ahi + ko, bhi + ko, idesc, (kb | k) ? 1u : 0u);
-                        umma_bf16(tcx, ahi + ko, blo + ko, idesc, (kb | k) ? 1u : 0u);
+                        umma_bf16(td, ahi + ko, bhi + ko, idesc2, (kb | k) ? 1u : 0u);     // A_hi x [B_hi ; B_lo]
                         umma_bf16(tcx, alo + ko, bhi + ko, idesc, 1u);
                     }
                     umma_commit(empty(s));
@@ -405,6 +425,262 @@ conv_tc_persist_kernel(const __grid_constant__ TcMaps maps, const TcParams p, fl
             if (c < p.Co) {
                 atomicAdd(stats + c, (double)stat_smem[c]);
                 atomicAdd(stats + p.Co + c, (double)stat_smem[256 + c]);
+            }
+        }
+    }
+}
+
+// =============================================================================================
+// Halo-patch variant for stride-1 1x3x3 convolutions over 64 channels (layer1 and its dgrads).
+//
+// The tap-per-box kernels above fetch every activation tile once per filter tap: 9 x 32 KB per 128
+// outputs, which saturates the L2 -> SM path (~43 B/clk/SM) long before the tensor pipe (measured: layer1
+// conv 35 % tensor-active, 77 GB/s/SM of TMA traffic).  Here ONE TMA box per tile brings the whole input
+// patch -- `bhr` image rows x (W + 2) pixels, halo columns / rows zero-filled by the TMA -- into shared
+// memory, and the nine taps are nine UMMA descriptors into that same patch:
+//
+//   * a tile is 128 consecutive positions of the frame in "padded-pitch" order f = h * PW + w, PW = W + 2
+//     (positions with w >= W are computed and dropped: 2 / PW of the MMA work);
+//   * the patch row of output f under tap (dh, dw) is (f - f0) + rowoff + dh * PW + dw, a CONSTANT row
+//     shift per tap, so the K-major SW128 descriptor just starts `shift * 128` bytes further in (the
+//     128B swizzle is a function of the absolute shared-memory address, which TMA and UMMA share; the
+//     descriptor's base-offset field stays 0 -- measured: bit-exact against the tap-per-box kernel);
+//   * weights stream through a ring of per-tap [B_hi ; B_lo] tiles; the two are adjacent, so
+//     A_hi x [B_hi ; B_lo] is ONE N = 2*BN instruction writing the main and the cross-term accumulator.
+// =============================================================================================
+struct HaloParams {
+    int PW, bhr;               // padded row pitch (W + 2) and image rows per patch box
+    int H, W, T;               // frame extents, frames per clip
+    int tiles_per_frame, total_tiles;
+    int patch_bytes;           // one plane of the patch, rounded up to 1024
+    int bstages;               // weight ring depth
+    int BN, Co, Ksrc;
+    int shift[9], kcol[9];     // per tap: patch row shift, column of the packed filter matrix
+    long long out_sn, out_st, out_sh, out_sw, out_base;
+};
+
+constexpr int HALO_BN = 64, HALO_STAGES = 6;
+
+// MMAs of one tile: 9 taps x 4 k-steps x {A_hi x [B_hi ; B_lo] (N = 128), A_lo x B_hi (N = 64)}.  S0 = ring stage of
+// tap 0.  Descriptors are built from their low words (start address >> 4 | LBO field); the high word of a
+// K-major SWIZZLE_128B descriptor (SBO = 1024 B, version 1, layout 2) is the constant 0x40004040.
+template <int S0>
+__device__ __forceinline__ void halo_issue_tile(uint32_t a_lo, const uint32_t (&sh16)[9], uint32_t patch16, uint32_t ring_lo,
+                                                uint32_t td, uint32_t tcx, uint32_t idesc2, uint32_t idesc1,
+                                                uint32_t bfull0, uint32_t bempty0, uint32_t& ph, uint32_t tmfull) {
+    constexpr uint64_t DHI = 0x40004040ull << 32;
+#pragma unroll
+    for (int t = 0; t < 9; ++t) {
+        const int s = (S0 + t) % HALO_STAGES;
+        mbar_wait(bfull0 + 8u * s, ph);
+        tc_fence_after();
+        const uint32_t ahi = a_lo + sh16[t], alo = ahi + patch16, b = ring_lo + (uint32_t)s * (2u * HALO_BN * 128u / 16u);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            umma_bf16(td, DHI | (uint64_t)(ahi + 2 * k), DHI | (uint64_t)(b + 2 * k), idesc2, (t | k) ? 1u : 0u);
+            umma_bf16(tcx, DHI | (uint64_t)(alo + 2 * k), DHI | (uint64_t)(b + 2 * k), idesc1, 1u);
+        }
+        if (s & 1) umma_commit(bempty0 + 8u * (s >> 1));            // releases stages s-1 and s
+        if (s == HALO_STAGES - 1) ph ^= 1u;
+    }
+    umma_commit(tmfull);
+}
+
+__global__ void __launch_bounds__(320, 1)
+conv_tc_halo_kernel(const __grid_constant__ TcMaps maps, const HaloParams hp, float* __restrict__ y, int accumulate,
+                    double* __restrict__ stats) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t b_tile = (uint32_t)hp.BN * 128u;
+    // smem: [2 x (patch_hi | patch_lo)] [bstages x (B_hi | B_lo)] [barriers] [BN partials]
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t pbuf = 2u * (uint32_t)hp.patch_bytes;
+    const uint32_t ring = base + 2u * pbuf;
+    const uint32_t bar_base = ring + (uint32_t)hp.bstages * 2u * b_tile;
+    auto p_full = [&](int b) { return bar_base + 8u * b; };
+    auto p_empty = [&](int b) { return bar_base + 8u * (2 + b); };
+    auto tm_full = [&](int b) { return bar_base + 8u * (4 + b); };
+    auto tm_empty = [&](int b) { return bar_base + 8u * (6 + b); };
+    auto b_full = [&](int s) { return bar_base + 8u * (8 + s); };
+    auto b_empty = [&](int s) { return bar_base + 8u * (8 + hp.bstages + s); };
+    const uint32_t tmem_ptr_addr = bar_base + 8u * (8 + 2 * hp.bstages);
+    float* stat_smem = reinterpret_cast<float*>(smem_raw + (bar_base + 8u * (9 + 2 * hp.bstages) - smem_u32(smem_raw)));
+    if (stats)
+        for (int i = threadIdx.x; i < 512; i += blockDim.x) stat_smem[i] = 0.f;
+    const uint32_t tmem_cols = 4u * (uint32_t)hp.BN;
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.a_hi[0]) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.a_lo[0]) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.b_hi) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.b_lo) : "memory");
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(p_full(b), 1); mbar_init(p_empty(b), 1);
+            mbar_init(tm_full(b), 1); mbar_init(tm_empty(b), 8);
+        }
+        for (int s = 0; s < hp.bstages; ++s) { mbar_init(b_full(s), 1); mbar_init(b_empty(s), 1); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) tmem_alloc(tmem_ptr_addr, tmem_cols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *reinterpret_cast<const uint32_t*>(smem_raw + (tmem_ptr_addr - smem_u32(smem_raw)));
+    const int my_tiles = ((int)blockIdx.x < hp.total_tiles) ? (hp.total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+
+    // tile i of this CTA -> frame (n, t), first padded-pitch position f0, first image row of the tile
+    auto tile_origin = [&](int i, int& n, int& t, int& f0, int& hrow0) {
+        const int tile = (int)blockIdx.x + i * (int)gridDim.x;
+        const int frame = tile / hp.tiles_per_frame;
+        f0 = (tile - frame * hp.tiles_per_frame) * 128;
+        hrow0 = f0 / hp.PW;
+        n = frame / hp.T; t = frame - n * hp.T;
+    };
+
+    // A tcgen05.commit drains the tensor pipe (measured with scripts/umma_bench.cu: ~155 cycles per commit, against
+    // 448 cycles of MMAs per tap), so commits are rationed: weight stages are released in PAIRS (one commit per two
+    // taps, counted across tile boundaries), and the end-of-tile commit on tm_full doubles as the "patch buffer is
+    // free" signal for the producer.
+    if (warp == 0) {
+        if (elect_one()) {
+            const uint32_t patch_tx = 2u * (uint32_t)(hp.bhr * hp.PW) * 128u;
+            int next_patch = 0;                      // next tile whose patch has not been requested yet
+            auto try_patch = [&](bool block) {
+                const int b = next_patch & 1;
+                if (next_patch >= 2) {               // buffer b was last read by tile next_patch - 2
+                    const uint32_t par = ((uint32_t)(next_patch - 2) >> 1) & 1u;
+                    if (block) {
+                        mbar_wait(tm_full(b), par);
+                    } else {
+                        uint32_t ok;
+                        asm volatile(
+                            "{\n\t.reg .pred P1;\n\t"
+                            "mbarrier.test_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
+                            "selp.u32 %0, 1, 0, P1;\n\t}" : "=r"(ok) : "r"(tm_full(b)), "r"(par) : "memory");
+                        if (!ok) return;
+                    }
+                }
+                int n, t, f0, hrow0;
+                tile_origin(next_patch, n, t, f0, hrow0);
+                mbar_expect_tx(p_full(b), patch_tx);
+                tma_load_5d(&maps.a_hi[0], base + b * pbuf, p_full(b), 0, -1, hrow0 - 1, t, n);
+                tma_load_5d(&maps.a_lo[0], base + b * pbuf + hp.patch_bytes, p_full(b), 0, -1, hrow0 - 1, t, n);
+                ++next_patch;
+            };
+            if (my_tiles > 0) try_patch(true);
+            int s = 0; uint32_t ph = 0;
+            for (int i = 0; i < my_tiles; ++i) {
+                for (int tap = 0; tap < 9; ++tap) {
+                    // the patch of tile i+1 reuses the buffer of tile i-1: request it as soon as that tile has
+                    // retired, without stalling the weight ring (the last tap blocks, so it is never skipped)
+                    if (next_patch <= i + 1 && next_patch < my_tiles) try_patch(tap == 8);
+                    if ((s & 1) == 0) mbar_wait(b_empty(s >> 1), ph ^ 1u);
+                    mbar_expect_tx(b_full(s), 2u * b_tile);
+                    const uint32_t sb = ring + (uint32_t)s * 2u * b_tile;
+                    tma_load_2d(&maps.b_hi, sb, b_full(s), hp.kcol[tap], 0);
+                    tma_load_2d(&maps.b_lo, sb + b_tile, b_full(s), hp.kcol[tap], 0);
+                    if (++s == hp.bstages) { s = 0; ph ^= 1u; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (elect_one()) {
+            // D = f32, A = B = bf16, K-major; M = 128; N = 2*BN for A_hi x [B_hi ; B_lo], N = BN for A_lo x B_hi
+            const uint32_t idesc_n = (1u << 4) | (1u << 7) | (1u << 10) | ((128u >> 4) << 24);
+            const uint32_t idesc2 = idesc_n | ((uint32_t)((2 * hp.BN) >> 3) << 17);
+            const uint32_t idesc1 = idesc_n | ((uint32_t)(hp.BN >> 3) << 17);
+            // One thread issues every MMA, in order, so its own instruction latency is on the critical path: with
+            // ~75 dependent instructions per tap the tensor pipe idled ~45 % of the time (measured; weights, patch
+            // traffic, stores and commit count all ruled out).  The per-tile body is therefore fully unrolled with
+            // compile-time stage indices (6 stages, 9 taps: the ring phase repeats every two tiles) and 32-bit
+            // descriptor arithmetic only.
+            uint32_t sh16[9];
+#pragma unroll
+            for (int t = 0; t < 9; ++t) sh16[t] = (uint32_t)hp.shift[t] * 8u;
+            const uint32_t patch16 = (uint32_t)hp.patch_bytes >> 4;
+            const uint32_t ring_lo = (ring >> 4) | 0x10000u;
+            const uint32_t bfull0 = b_full(0), bempty0 = b_empty(0);
+            uint32_t ph = 0;
+            for (int i = 0; i < my_tiles; ++i) {
+                const int buf = i & 1;
+                const uint32_t td = tmem_base + (uint32_t)(buf * 2 * HALO_BN), tcx = td + (uint32_t)HALO_BN;
+                int n, t, f0, hrow0;
+                tile_origin(i, n, t, f0, hrow0);
+                const uint32_t a_lo = ((base + buf * pbuf + (uint32_t)(f0 - hrow0 * hp.PW) * 128u) >> 4) | 0x10000u;
+                mbar_wait(tm_empty(buf), (((uint32_t)i >> 1) & 1u) ^ 1u);
+                mbar_wait(p_full(buf), ((uint32_t)i >> 1) & 1u);
+                if (i & 1) halo_issue_tile<3>(a_lo, sh16, patch16, ring_lo, td, tcx, idesc2, idesc1, bfull0, bempty0, ph, tm_full(buf));
+                else       halo_issue_tile<0>(a_lo, sh16, patch16, ring_lo, td, tcx, idesc2, idesc1, bfull0, bempty0, ph, tm_full(buf));
+            }
+        }
+    } else {
+        // epilogue: 8 warps = 4 TMEM lane quarters (warp % 4) x two 32-column halves.  Both accumulator loads are
+        // in flight together and the TMEM buffer is handed back before the global stores; the BatchNorm partial
+        // sums stay in registers (one row per lane) across all tiles of the CTA and are transposed once at the end.
+        const int q = warp & 3, c0 = ((warp - 2) >> 2) * 32;
+        float rs[32], rq[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) { rs[j] = 0.f; rq[j] = 0.f; }
+        for (int i = 0; i < my_tiles; ++i) {
+            const int buf = i & 1;
+            const uint32_t td = tmem_base + (uint32_t)(buf * 2 * hp.BN), tcx = td + (uint32_t)hp.BN;
+            int n, t, f0, hrow0;
+            tile_origin(i, n, t, f0, hrow0);
+            const int f = f0 + q * 32 + lane;
+            const int h = f / hp.PW, w = f - h * hp.PW;
+            const bool valid = h < hp.H && w < hp.W;
+            const long long row = (long long)n * hp.out_sn + (long long)t * hp.out_st + (long long)h * hp.out_sh +
+                                  (long long)w * hp.out_sw + hp.out_base;
+            mbar_wait(tm_full(buf), ((uint32_t)i >> 1) & 1u);
+            tc_fence_after();
+            uint32_t v[32], u[32];
+            tmem_ld32_nowait(td + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+            tmem_ld32_nowait(tcx + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, u);
+            tmem_ld_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tm_empty(buf));
+            if (valid) {
+                float4* dst = reinterpret_cast<float4*>(y + row * hp.Co + c0);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    float4 o = make_float4(__uint_as_float(v[4 * j]) + __uint_as_float(u[4 * j]),
+                                           __uint_as_float(v[4 * j + 1]) + __uint_as_float(u[4 * j + 1]),
+                                           __uint_as_float(v[4 * j + 2]) + __uint_as_float(u[4 * j + 2]),
+                                           __uint_as_float(v[4 * j + 3]) + __uint_as_float(u[4 * j + 3]));
+                    if (stats) {
+                        rs[4 * j] += o.x; rs[4 * j + 1] += o.y; rs[4 * j + 2] += o.z; rs[4 * j + 3] += o.w;
+                        rq[4 * j] += o.x * o.x; rq[4 * j + 1] += o.y * o.y; rq[4 * j + 2] += o.z * o.z; rq[4 * j + 3] += o.w * o.w;
+                    }
+                    if (accumulate) { const float4 c = dst[j]; o.x += c.x; o.y += c.y; o.z += c.z; o.w += c.w; }
+                    dst[j] = o;
+                }
+            }
+        }
+        if (stats) {
+            // lane l ends up with column c0 + l summed over the warp's 32 rows (31-shuffle transposing butterfly)
+#pragma unroll
+            for (int off = 16; off >= 1; off >>= 1) {
+                const bool up = (lane & off) != 0;
+#pragma unroll
+                for (int i = 0; i < off; ++i) {
+                    const float s_send = up ? rs[i] : rs[i + off], s_keep = up ? rs[i + off] : rs[i];
+                    const float q_send = up ? rq[i] : rq[i + off], q_keep = up ? rq[i + off] : rq[i];
+                    rs[i] = s_keep + __shfl_xor_sync(0xffffffffu, s_send, off);
+                    rq[i] = q_keep + __shfl_xor_sync(0xffffffffu, q_send, off);
+                }
+            }
+            atomicAdd(&stat_smem[c0 + lane], rs[0]);
+            atomicAdd(&stat_smem[256 + c0 + lane], rq[0]);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, tmem_cols);
+    if (stats) {
+        for (int c = threadIdx.x; c < hp.BN; c += blockDim.x) {
+            if (c < hp.Co) {
+                atomicAdd(stats + c, (double)stat_smem[c]);
+                atomicAdd(stats + hp.Co + c, (double)stat_smem[256 + c]);
             }
         }
     }
@@ -680,6 +956,69 @@ int make_parity_views(TcMaps& maps, const dpc_conv_geom* g, const void* x_hi, co
     return DPC_OK;
 }
 
+// Halo-patch schedule (conv_tc_halo_kernel) for a stride-1 1x3x3 conv over a 64-channel tensor `src`
+// [NB,T,H,W,64] (x for the forward, dy for the dgrad) with 64 output channels.  `tH` / `tW` are the tap tables of
+// the caller (forward or flipped), `wp_*` the matching packed filter planes [64][9][64].
+// Returns 1 if it launched, 0 if the shape is not eligible, < 0 on error.
+int try_conv_halo(const void* src_hi, const void* src_lo, const void* wp_hi, const void* wp_lo, int NB, int T, int H,
+                  int W, const TapDim& tH, const TapDim& tW, float* y, int accumulate, double* stats, cudaStream_t st) {
+    if (const char* e = getenv("DPC_TC_HALO")) if (!atoi(e)) return 0;
+    HaloParams hp;
+    memset(&hp, 0, sizeof(hp));
+    hp.PW = W + 2;
+    hp.bhr = 3 + (129 + hp.PW - 1) / hp.PW;
+    if (hp.PW > 256 || hp.bhr > 256 || tH.count != 3 || tW.count != 3) return 0;
+    hp.H = H; hp.W = W; hp.T = T;
+    hp.tiles_per_frame = (H * hp.PW + 127) / 128;
+    const long long total = (long long)NB * T * hp.tiles_per_frame;
+    // padded-pitch tiles waste the halo columns and the tail of the last tile of a frame
+    if ((double)H * W < 0.6 * 128.0 * hp.tiles_per_frame || total >= (1ll << 31)) return 0;
+    hp.total_tiles = (int)total;
+    hp.patch_bytes = ((hp.bhr * hp.PW * 128 + 1023) / 1024) * 1024;
+    hp.BN = 64; hp.Co = 64; hp.Ksrc = 64;
+    const size_t b_stage = 2 * 64 * 128, budget = 225 * 1024;
+    const size_t fixed = 4 * (size_t)hp.patch_bytes + 1024 + 2048 + 256;
+    if (fixed + 2 * b_stage > budget) return 0;
+    if ((int)((budget - fixed) / b_stage) < HALO_STAGES) return 0;   // the kernel is written for a 6-stage weight ring
+    hp.bstages = HALO_STAGES;
+    for (int ih = 0; ih < 3; ++ih)
+        for (int iw = 0; iw < 3; ++iw) {
+            if (tH.off[ih] < -1 || tH.off[ih] > 1 || tW.off[iw] < -1 || tW.off[iw] > 1) return 0;
+            hp.shift[ih * 3 + iw] = (tH.off[ih] + 1) * hp.PW + (tW.off[iw] + 1);
+            hp.kcol[ih * 3 + iw] = (tH.k[ih] * 3 + tW.k[iw]) * 64;
+        }
+    hp.out_sw = 1; hp.out_sh = W; hp.out_st = (long long)H * W; hp.out_sn = (long long)T * H * W; hp.out_base = 0;
+    TcMaps maps;
+    const uint32_t box[5] = {64, (uint32_t)hp.PW, (uint32_t)hp.bhr, 1, 1};
+    const long long sw = 64, sh = (long long)W * sw, sT = (long long)H * sh, sn = (long long)T * sT;
+    if (make_act_map(&maps.a_hi[0], src_hi, 64, W, H, T, NB, sw, sh, sT, sn, box)) return -1;
+    if (make_act_map(&maps.a_lo[0], src_lo, 64, W, H, T, NB, sw, sh, sT, sn, box)) return -1;
+    const uint64_t bd[2] = {(uint64_t)9 * 64, 64};
+    const uint64_t bs[1] = {(uint64_t)9 * 64 * 2};
+    const uint32_t bb[2] = {64, 64};
+    if (make_map(&maps.b_hi, wp_hi, 2, bd, bs, bb)) return -1;
+    if (make_map(&maps.b_lo, wp_lo, 2, bd, bs, bb)) return -1;
+    const size_t smem = 4 * (size_t)hp.patch_bytes + hp.bstages * b_stage + 8 * (9 + 2 * hp.bstages) + 2048 + 1024;
+    if (cudaFuncSetAttribute(conv_tc_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+        dpc_set_error("conv_tc_halo_kernel: cannot reserve %zu bytes of shared memory", smem);
+        return -1;
+    }
+    const int sms = dpc_num_sms();
+    const int grid = hp.total_tiles < sms ? hp.total_tiles : sms;
+    conv_tc_halo_kernel<<<grid, 320, smem, st>>>(maps, hp, y, accumulate, stats);
+    dpc_count_launch(1);
+    if (cudaError_t e = cudaGetLastError()) {
+        dpc_set_error("conv_tc_halo_kernel launch: %s", cudaGetErrorString(e));
+        return -1;
+    }
+    return 1;
+}
+
+bool halo_eligible(const dpc_conv_geom* g) {
+    return g->kT == 1 && g->kH == 3 && g->kW == 3 && g->sT == 1 && g->sH == 1 && g->sW == 1 && g->pT == 0 && g->pH == 1 &&
+           g->pW == 1 && g->Ci == 64 && g->Co == 64;
+}
+
 int launch_conv(TcLaunch& L, float* y, int accumulate, cudaStream_t st, double* stats = nullptr) {
     const TcParams& p = L.p;
     const int total_tiles = (int)L.grid.x;
@@ -837,6 +1176,13 @@ extern "C" int dpc_conv3d_fwd_tc(const dpc_conv_geom* g, const void* x_hi, const
     fwd_taps(p.tT, g->kT, g->sT, g->pT); fwd_taps(p.tH, g->kH, g->sH, g->pH); fwd_taps(p.tW, g->kW, g->sW, g->pW);
     p.kH = g->kH; p.kW = g->kW; p.sH = g->sH; p.sW = g->sW; p.nviews = g->sT * g->sH * g->sW;
     p.cchunks = g->Ci / 64; p.Ksrc = g->Ci;
+    if (halo_eligible(g)) {
+        if (bn_ws) DPC_CUDA(cudaMemsetAsync(bn_ws, 0, sizeof(double) * 2 * g->Co, as_stream(stream)));
+        const int r = try_conv_halo(x_hi, x_lo, wf_hi, wf_lo, g->NB, g->To, g->Ho, g->Wo, p.tH, p.tW, y, 0, bn_ws,
+                                    as_stream(stream));
+        if (r < 0) return DPC_ERR_CUDA;
+        if (r > 0) return DPC_OK;
+    }
     set_tile_grid(p, g->NB, g->To, g->Ho, g->Wo, 128);
     p.Co = g->Co; p.BN = pick_bn(g->Co);
     const int taps = g->kT * g->kH * g->kW;
@@ -882,6 +1228,12 @@ extern "C" int dpc_conv3d_dgrad_tc(const dpc_conv_geom* g, const void* dy_hi, co
                 }
                 p.kH = g->kH; p.kW = g->kW; p.sH = 1; p.sW = 1; p.nviews = 1;
                 p.cchunks = g->Co / 64; p.Ksrc = g->Co;
+                if (halo_eligible(g)) {
+                    const int r = try_conv_halo(dy_hi, dy_lo, wd_hi, wd_lo, g->NB, g->Ti, g->Hi, g->Wi, p.tH, p.tW, dx,
+                                                accumulate, nullptr, as_stream(stream));
+                    if (r < 0) return DPC_ERR_CUDA;
+                    if (r > 0) continue;
+                }
                 set_tile_grid(p, g->NB, Tc, Hc, Wc, 128);
                 p.Co = g->Ci; p.BN = pick_bn(g->Ci);
                 set_stages(L, p.tT.count * p.tH.count * p.tW.count * p.cchunks);
