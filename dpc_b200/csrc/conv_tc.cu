@@ -687,6 +687,159 @@ conv_tc_halo_kernel(const __grid_constant__ TcMaps maps, const HaloParams hp, fl
 }
 
 // =============================================================================================
+// Halo-patch wgrad for the same sites (stride-1 1x3x3, 64 -> 64 channels):
+//
+//   dWp[co][tap][ci] = sum over positions  dY[pos, co] * X[pos (+) tap, ci]
+//
+// K = positions.  A tile is 128 consecutive padded-pitch positions of one frame (as in conv_tc_halo_kernel); ONE
+// box brings the X patch (halo included) and one the dY rows, whose out-of-frame columns w >= W and rows h >= H are
+// zero-filled by the TMA, so the dropped positions contribute nothing.  Both operands are MN-major views of those
+// boxes (a smem row = one position = 64 channels), and a filter tap is again a constant ROW shift of the X operand:
+//   A (M = 128) = X^T of TWO taps: the two 64-channel groups of the operand are `LBO` apart, and LBO is simply the
+//                 difference of the two taps' row shifts (9 taps = 4 pairs + 1 single, 5 accumulators of 64 columns);
+//   B (N = 64)  = dY^T.
+// The tap-per-box wgrad kernel fetches X once per tap and pads M = Co = 64 to 128 with zeros; this one fetches
+// X once and has no padding (layer1: 2.4 ms -> see profiles/).  All three split-BF16 products of a tap pair share
+// one TMEM accumulator (5 x 64 columns; a main/correction split would need 640), so the chain is flushed into the
+// fp32 result with atomics every `chain` tiles to bound the truncating in-TMEM accumulation.
+// =============================================================================================
+struct WgHaloParams {
+    int PW, bhr_x, bhr_y, H, W, T;
+    int tiles_per_frame, total_tiles;
+    int xpatch_bytes, ypatch_bytes;      // one plane, rounded up to 1024
+    int chain;                           // tiles per TMEM accumulation chain
+    int shift[9];                        // X row shift per tap
+};
+
+__global__ void __launch_bounds__(192, 1)
+wgrad_halo_kernel(const __grid_constant__ TcMaps maps, const WgHaloParams hp, float* __restrict__ dwp) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // smem: 2 x [x_hi | x_lo | dy_hi | dy_lo] [barriers]
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t bufsz = 2u * (uint32_t)hp.xpatch_bytes + 2u * (uint32_t)hp.ypatch_bytes;
+    const uint32_t bar_base = base + 2u * bufsz;
+    auto full = [&](int b) { return bar_base + 8u * b; };
+    auto empty = [&](int b) { return bar_base + 8u * (2 + b); };
+    const uint32_t acc_full = bar_base + 32u, acc_empty = bar_base + 40u, tmem_ptr_addr = bar_base + 48u;
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.a_hi[0]) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.a_lo[0]) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.b_hi) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.b_lo) : "memory");
+        for (int b = 0; b < 2; ++b) { mbar_init(full(b), 1); mbar_init(empty(b), 1); }
+        mbar_init(acc_full, 1);
+        mbar_init(acc_empty, 4);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) tmem_alloc(tmem_ptr_addr, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *reinterpret_cast<const uint32_t*>(smem_raw + (tmem_ptr_addr - smem_u32(smem_raw)));
+    const int my_tiles = ((int)blockIdx.x < hp.total_tiles) ? (hp.total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+    const int chains = (my_tiles + hp.chain - 1) / hp.chain;
+
+    auto tile_origin = [&](int i, int& n, int& t, int& f0, int& hrow0) {
+        const int tile = (int)blockIdx.x + i * (int)gridDim.x;
+        const int frame = tile / hp.tiles_per_frame;
+        f0 = (tile - frame * hp.tiles_per_frame) * 128;
+        hrow0 = f0 / hp.PW;
+        n = frame / hp.T; t = frame - n * hp.T;
+    };
+
+    if (warp == 0) {
+        if (elect_one()) {
+            const uint32_t tx = 2u * (uint32_t)(hp.bhr_x * hp.PW) * 128u + 2u * (uint32_t)(hp.bhr_y * hp.PW) * 128u;
+            for (int i = 0; i < my_tiles; ++i) {
+                const int b = i & 1;
+                int n, t, f0, hrow0;
+                tile_origin(i, n, t, f0, hrow0);
+                mbar_wait(empty(b), (((uint32_t)i >> 1) & 1u) ^ 1u);
+                mbar_expect_tx(full(b), tx);
+                const uint32_t sx = base + b * bufsz, sy = sx + 2u * hp.xpatch_bytes;
+                tma_load_5d(&maps.a_hi[0], sx, full(b), 0, -1, hrow0 - 1, t, n);
+                tma_load_5d(&maps.a_lo[0], sx + hp.xpatch_bytes, full(b), 0, -1, hrow0 - 1, t, n);
+                tma_load_5d(&maps.b_hi, sy, full(b), 0, 0, hrow0, t, n);
+                tma_load_5d(&maps.b_lo, sy + hp.ypatch_bytes, full(b), 0, 0, hrow0, t, n);
+            }
+        }
+    } else if (warp == 1) {
+        if (elect_one()) {
+            // D = f32, A = B = bf16, both MN-major (bits 15, 16), N = 64, M = 128
+            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((64u >> 3) << 17) | ((128u >> 4) << 24);
+            constexpr uint64_t DHI = 0x40004040ull << 32;     // SBO = 1024 B, version 1, SWIZZLE_128B
+            // low descriptor word of a tap pair relative to the patch: first tap's row shift | LBO = shift difference
+            uint32_t pair_lo[5];
+#pragma unroll
+            for (int p = 0; p < 5; ++p) {
+                const int a = 2 * p, b = (2 * p + 1 < 9) ? 2 * p + 1 : a;
+                pair_lo[p] = (uint32_t)hp.shift[a] * 8u + (((uint32_t)(hp.shift[b] - hp.shift[a]) * 8u) << 16);
+            }
+            const uint32_t xpatch16 = (uint32_t)hp.xpatch_bytes >> 4, ypatch16 = (uint32_t)hp.ypatch_bytes >> 4;
+            for (int i = 0; i < my_tiles; ++i) {
+                const int b = i & 1;
+                const int in_chain = i % hp.chain;
+                int n, t, f0, hrow0;
+                tile_origin(i, n, t, f0, hrow0);
+                const uint32_t rowoff16 = (uint32_t)(f0 - hrow0 * hp.PW) * 8u;
+                const uint32_t x16 = ((base + b * bufsz) >> 4) + rowoff16;
+                const uint32_t y16 = (((base + b * bufsz + 2u * hp.xpatch_bytes) >> 4) + rowoff16) | (512u << 16);
+                if (in_chain == 0 && i > 0) {                   // the previous chain must have been drained
+                    mbar_wait(acc_empty, (((uint32_t)(i / hp.chain) - 1u) & 1u));
+                }
+                mbar_wait(full(b), ((uint32_t)i >> 1) & 1u);
+                tc_fence_after();
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {                   // UMMA_K = 16 positions = 2048 B of rows
+                    const uint64_t yhi = DHI | (uint64_t)(y16 + k * 128), ylo = DHI | (uint64_t)(y16 + ypatch16 + k * 128);
+#pragma unroll
+                    for (int p = 0; p < 5; ++p) {
+                        const uint64_t xhi = DHI | (uint64_t)(x16 + pair_lo[p] + k * 128);
+                        const uint64_t xlo = DHI | (uint64_t)(x16 + xpatch16 + pair_lo[p] + k * 128);
+                        const uint32_t d = tmem_base + (uint32_t)(p * 64);
+                        umma_bf16(d, xhi, yhi, idesc, (in_chain | k) ? 1u : 0u);
+                        umma_bf16(d, xhi, ylo, idesc, 1u);
+                        umma_bf16(d, xlo, yhi, idesc, 1u);
+                    }
+                }
+                umma_commit(empty(b));
+                if (in_chain == hp.chain - 1 || i == my_tiles - 1) umma_commit(acc_full);
+            }
+        }
+    } else {
+        // drain: TMEM lane = (tap of the pair, ci); column = co
+        const int q = warp & 3;
+        const int m = q * 32 + lane, g = m >> 6, ci = m & 63;
+        for (int c = 0; c < chains; ++c) {
+            mbar_wait(acc_full, (uint32_t)c & 1u);
+            tc_fence_after();
+#pragma unroll 1
+            for (int p = 0; p < 5; ++p) {
+                const int tap = 2 * p + g;
+                uint32_t v[32], u[32];
+                tmem_ld32_nowait(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(p * 64), v);
+                tmem_ld32_nowait(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(p * 64 + 32), u);
+                tmem_ld_wait();
+                if (tap < 9) {
+                    float* o = dwp + (size_t)tap * 64 + ci;
+#pragma unroll
+                    for (int co = 0; co < 32; ++co) atomicAdd(o + (size_t)co * 576, __uint_as_float(v[co]));
+#pragma unroll
+                    for (int co = 0; co < 32; ++co) atomicAdd(o + (size_t)(co + 32) * 576, __uint_as_float(u[co]));
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(acc_empty);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+// =============================================================================================
 // wgrad:  dW[co][tap][ci] += sum_{positions} dY[pos, co] * X[pos (+) tap, ci]
 //   A = dY^T (M = co, K = positions), B = X^T (N = ci, K = positions): both MN-major over the
 //   same [positions x 64 channels] TMA boxes.  grid = (co tiles * ci tiles, taps, splits);
@@ -1014,6 +1167,52 @@ int try_conv_halo(const void* src_hi, const void* src_lo, const void* wp_hi, con
     return 1;
 }
 
+// Halo-patch wgrad (wgrad_halo_kernel) for a stride-1 1x3x3 64 -> 64 site; accumulates into the zeroed `dwp`.
+// Returns 1 if it launched, 0 if the shape is not eligible, < 0 on error.
+int try_wgrad_halo(const void* x_hi, const void* x_lo, const void* dy_hi, const void* dy_lo, int NB, int T, int H, int W,
+                   float* dwp, cudaStream_t st) {
+    if (const char* e = getenv("DPC_TC_HALO")) if (!atoi(e)) return 0;
+    WgHaloParams hp;
+    memset(&hp, 0, sizeof(hp));
+    hp.PW = W + 2;
+    hp.bhr_x = 3 + (129 + hp.PW - 1) / hp.PW;
+    hp.bhr_y = (127 + 2 * hp.PW - 1) / hp.PW;                  // rows [rowoff, rowoff + 128), rowoff < PW
+    if (hp.PW > 256 || hp.bhr_x > 256) return 0;
+    hp.H = H; hp.W = W; hp.T = T;
+    hp.tiles_per_frame = (H * hp.PW + 127) / 128;
+    const long long total = (long long)NB * T * hp.tiles_per_frame;
+    if ((double)H * W < 0.6 * 128.0 * hp.tiles_per_frame || total >= (1ll << 31)) return 0;
+    hp.total_tiles = (int)total;
+    hp.xpatch_bytes = ((hp.bhr_x * hp.PW * 128 + 1023) / 1024) * 1024;
+    hp.ypatch_bytes = ((hp.bhr_y * hp.PW * 128 + 1023) / 1024) * 1024;
+    const size_t smem = 2 * (2 * (size_t)hp.xpatch_bytes + 2 * (size_t)hp.ypatch_bytes) + 64 + 1024;
+    if (smem > 227 * 1024) return 0;
+    hp.chain = 64;              // 64 tiles x 8 k-steps x 3 products = 1536 truncating accumulations per chain
+    for (int kh = 0; kh < 3; ++kh)
+        for (int kw = 0; kw < 3; ++kw) hp.shift[kh * 3 + kw] = kh * hp.PW + kw;     // x(h + kh - 1, w + kw - 1)
+    TcMaps maps;
+    const long long sw = 64, sh = (long long)W * sw, sT = (long long)H * sh, sn = (long long)T * sT;
+    const uint32_t bx[5] = {64, (uint32_t)hp.PW, (uint32_t)hp.bhr_x, 1, 1};
+    const uint32_t by[5] = {64, (uint32_t)hp.PW, (uint32_t)hp.bhr_y, 1, 1};
+    if (make_act_map(&maps.a_hi[0], x_hi, 64, W, H, T, NB, sw, sh, sT, sn, bx)) return -1;
+    if (make_act_map(&maps.a_lo[0], x_lo, 64, W, H, T, NB, sw, sh, sT, sn, bx)) return -1;
+    if (make_act_map(&maps.b_hi, dy_hi, 64, W, H, T, NB, sw, sh, sT, sn, by)) return -1;
+    if (make_act_map(&maps.b_lo, dy_lo, 64, W, H, T, NB, sw, sh, sT, sn, by)) return -1;
+    if (cudaFuncSetAttribute(wgrad_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+        dpc_set_error("wgrad_halo_kernel: cannot reserve %zu bytes of shared memory", smem);
+        return -1;
+    }
+    const int sms = dpc_num_sms();
+    const int grid = hp.total_tiles < sms ? hp.total_tiles : sms;
+    wgrad_halo_kernel<<<grid, 192, smem, st>>>(maps, hp, dwp);
+    dpc_count_launch(1);
+    if (cudaError_t e = cudaGetLastError()) {
+        dpc_set_error("wgrad_halo_kernel launch: %s", cudaGetErrorString(e));
+        return -1;
+    }
+    return 1;
+}
+
 bool halo_eligible(const dpc_conv_geom* g) {
     return g->kT == 1 && g->kH == 3 && g->kW == 3 && g->sT == 1 && g->sH == 1 && g->sW == 1 && g->pT == 0 && g->pH == 1 &&
            g->pW == 1 && g->Ci == 64 && g->Co == 64;
@@ -1261,6 +1460,18 @@ extern "C" int dpc_conv3d_wgrad_tc(const dpc_conv_geom* g, const void* x_hi, con
     DPC_REQUIRE(x_hi && x_lo && dy_hi && dy_lo && dwp && dw, "dpc_conv3d_wgrad_tc: null pointer");
     cudaStream_t st = as_stream(stream);
     const int taps = g->kT * g->kH * g->kW;
+    if (halo_eligible(g)) {
+        DPC_CUDA(cudaMemsetAsync(dwp, 0, sizeof(float) * (size_t)g->Co * taps * g->Ci, st));
+        const int r = try_wgrad_halo(x_hi, x_lo, dy_hi, dy_lo, g->NB, g->To, g->Ho, g->Wo, dwp, st);
+        if (r < 0) return DPC_ERR_CUDA;
+        if (r > 0) {
+            const long long total = (long long)g->Co * g->Ci * taps;
+            const long long blocks = (total + 255) / 256, cap = (long long)dpc_num_sms() * 8;
+            unpack_wgrad_ctc_kernel<<<(int)(blocks < cap ? blocks : cap), 256, 0, st>>>(dwp, dw, g->Co, g->Ci, taps);
+            DPC_LAUNCH_CHECK();
+            return DPC_OK;
+        }
+    }
     TcLaunch L;
     memset(&L.p, 0, sizeof(L.p));
     TcParams& p = L.p;
