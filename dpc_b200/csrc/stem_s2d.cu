@@ -1,0 +1,318 @@
+// Stem convolution (conv1: 3 -> 64, 1x7x7, stride (1,2,2), pad (0,3,3)) as a STRIDE-1 4x4 convolution over the
+// 2x2 space-to-depth input, on the tcgen05 tensor cores.  sm_100a only.
+//
+//   y[ho,wo] = sum_{c,kh,kw} w[c,kh,kw] x[c, 2ho+kh-3, 2wo+kw-3]
+//            = sum_{a,b in 0..3} sum_{c,r,s} W2[a,b][c,r,s] X2[ho+a-2, wo+b-2][c,r,s]
+//   X2[h2,w2][(c,r,s)] = x[c, 2h2+r, 2w2+s],   W2[a,b][c,r,s] = w[c, 2a+r-1, 2b+s-1]  (0 where an index is -1)
+//
+// X2 is stored channels-last as split-bf16 planes with 16 channels per pixel (12 real + 4 zero): one pixel = one
+// 32-byte row = exactly one UMMA k-step (K = 16).  The forward kernel is then the halo-patch scheme of
+// conv_tc.cu: ONE TMA box (SWIZZLE_32B) brings the input patch of a 128-position tile, the 16 taps are 16
+// row-shifted K-major descriptors into it, the whole packed filter bank (16 taps x [W_hi ; W_lo] = 64 KB) is
+// resident in shared memory, and a tile costs 32 MMAs and ONE tcgen05.commit.  This replaces the CUDA-core
+// im2col build of stem_tc.cu (measured 7.8 ms at B = 128, issue-latency bound) by a TMA-fed kernel bounded by
+// the 5.4 GB output write.
+//
+// Replaces nn.Conv3d(3, 64, (1,7,7), stride (1,2,2), padding (0,3,3)) at backbone/resnet_2d3d.py:134-135.
+#include "tc_common.cuh"
+
+namespace {
+
+constexpr int S2D_CH = 16, S2D_TAPS = 16, S2D_BN = 64;
+constexpr uint32_t S2D_W_BYTES = S2D_TAPS * 2 * S2D_BN * 32;      // 64 KB: per tap [W_hi (64 rows) ; W_lo (64 rows)] x 32 B
+
+struct S2dMaps { CUtensorMap x_hi, x_lo, w; };
+
+struct S2dParams {
+    int PW, bhr;               // padded row pitch (Wo + 3) and rows per patch box
+    int Ho, Wo, T;
+    int tiles_per_frame, total_tiles;
+    int patch_bytes;           // one plane of the patch, rounded up to 1024
+    int shift[S2D_TAPS];       // patch row shift per tap
+};
+
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+
+// x [NB,3,T,H,W] fp32 -> X2 planes [NB,T,H/2,W/2,16] bf16 (hi = bf16(v), lo = bf16(v - hi))
+__global__ void stem_s2d_pack_kernel(const float* __restrict__ x, uint4* __restrict__ hi, uint4* __restrict__ lo, int NB,
+                                     int T, int H, int W) {
+    const int H2 = H >> 1, W2 = W >> 1;
+    const long long total = (long long)NB * T * H2 * W2;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int w2 = (int)(i % W2);
+        const int h2 = (int)((i / W2) % H2);
+        const int t = (int)((i / ((long long)W2 * H2)) % T);
+        const int n = (int)(i / ((long long)W2 * H2 * T));
+        uint32_t ph[8], pl[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { ph[j] = 0u; pl[j] = 0u; }
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+                const float2 v = *reinterpret_cast<const float2*>(x + ((((size_t)n * 3 + c) * T + t) * H + 2 * h2 + r) * W + 2 * w2);
+                const __nv_bfloat16 h0 = __float2bfloat16_rn(v.x), h1 = __float2bfloat16_rn(v.y);
+                const __nv_bfloat16 l0 = __float2bfloat16_rn(v.x - __bfloat162float(h0));
+                const __nv_bfloat16 l1 = __float2bfloat16_rn(v.y - __bfloat162float(h1));
+                ph[c * 2 + r] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+                pl[c * 2 + r] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+            }
+        hi[2 * i] = make_uint4(ph[0], ph[1], ph[2], ph[3]);
+        hi[2 * i + 1] = make_uint4(ph[4], ph[5], ph[6], ph[7]);
+        lo[2 * i] = make_uint4(pl[0], pl[1], pl[2], pl[3]);
+        lo[2 * i + 1] = make_uint4(pl[4], pl[5], pl[6], pl[7]);
+    }
+}
+
+// w [64,3,1,7,7] fp32 -> wp [16 taps][hi | lo][64 co][16 ch] bf16
+__global__ void stem_s2d_wpack_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ wp) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= S2D_TAPS * S2D_BN * S2D_CH) return;
+    const int ch = i % S2D_CH, co = (i / S2D_CH) % S2D_BN, tap = i / (S2D_CH * S2D_BN);
+    const int a = tap >> 2, b = tap & 3;
+    float v = 0.f;
+    if (ch < 12) {
+        const int c = ch >> 2, r = (ch >> 1) & 1, s = ch & 1;
+        const int kh = 2 * a + r - 1, kw = 2 * b + s - 1;
+        if (kh >= 0 && kw >= 0) v = w[(co * 3 + c) * 49 + kh * 7 + kw];
+    }
+    const __nv_bfloat16 h = __float2bfloat16_rn(v);
+    const __nv_bfloat16 l = __float2bfloat16_rn(v - __bfloat162float(h));
+    wp[((size_t)(tap * 2 + 0) * S2D_BN + co) * S2D_CH + ch] = h;
+    wp[((size_t)(tap * 2 + 1) * S2D_BN + co) * S2D_CH + ch] = l;
+}
+
+// K-major SWIZZLE_32B descriptors: rows of 32 bytes, 8-row atoms 256 bytes apart.  High word = SBO (256 >> 4) |
+// version 1 (bit 46) | layout type 6 (SWIZZLE_32B, bits 61-63); low word = start address >> 4 | LBO field (unused).
+constexpr uint64_t S2D_DHI = 0xC0004010ull << 32;
+
+__global__ void __launch_bounds__(320, 1)
+stem_s2d_fwd_kernel(const __grid_constant__ S2dMaps maps, const S2dParams hp, float* __restrict__ y, double* __restrict__ stats) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // smem: [filter bank 64 KB] [2 x (patch_hi | patch_lo)] [barriers] [BN partials]
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t pbase = base + S2D_W_BYTES;
+    const uint32_t pbuf = 2u * (uint32_t)hp.patch_bytes;
+    const uint32_t bar_base = pbase + 2u * pbuf;
+    auto p_full = [&](int b) { return bar_base + 8u * b; };
+    auto tm_full = [&](int b) { return bar_base + 8u * (2 + b); };
+    auto tm_empty = [&](int b) { return bar_base + 8u * (4 + b); };
+    const uint32_t w_full = bar_base + 48u, tmem_ptr_addr = bar_base + 56u;
+    float* stat_smem = reinterpret_cast<float*>(smem_raw + (bar_base + 64u - smem_u32(smem_raw)));
+    if (stats && threadIdx.x < 128) stat_smem[threadIdx.x] = 0.f;
+    const uint32_t tmem_cols = 4u * S2D_BN;
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.x_hi) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.x_lo) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.w) : "memory");
+        for (int b = 0; b < 2; ++b) { mbar_init(p_full(b), 1); mbar_init(tm_full(b), 1); mbar_init(tm_empty(b), 8); }
+        mbar_init(w_full, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) tmem_alloc(tmem_ptr_addr, tmem_cols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *reinterpret_cast<const uint32_t*>(smem_raw + (tmem_ptr_addr - smem_u32(smem_raw)));
+    const int my_tiles = ((int)blockIdx.x < hp.total_tiles) ? (hp.total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+
+    // tile i of this CTA -> frame (n, t), first padded-pitch position f0, first output row of the tile
+    auto tile_origin = [&](int i, int& n, int& t, int& f0, int& hrow0) {
+        const int tile = (int)blockIdx.x + i * (int)gridDim.x;
+        const int frame = tile / hp.tiles_per_frame;
+        f0 = (tile - frame * hp.tiles_per_frame) * 128;
+        hrow0 = f0 / hp.PW;
+        n = frame / hp.T; t = frame - n * hp.T;
+    };
+
+    if (warp == 0) {
+        if (elect_one() && my_tiles > 0) {
+            mbar_expect_tx(w_full, S2D_W_BYTES);
+            for (int j = 0; j < 8; ++j) tma_load_2d(&maps.w, base + j * 8192, w_full, 0, j * 256);
+            const uint32_t patch_tx = 2u * (uint32_t)(hp.bhr * hp.PW) * 32u;
+            for (int i = 0; i < my_tiles; ++i) {
+                const int b = i & 1;
+                if (i >= 2) mbar_wait(tm_full(b), ((uint32_t)(i - 2) >> 1) & 1u);      // tile i-2 has retired: buffer free
+                int n, t, f0, hrow0;
+                tile_origin(i, n, t, f0, hrow0);
+                mbar_expect_tx(p_full(b), patch_tx);
+                tma_load_5d(&maps.x_hi, pbase + b * pbuf, p_full(b), 0, -2, hrow0 - 2, t, n);
+                tma_load_5d(&maps.x_lo, pbase + b * pbuf + hp.patch_bytes, p_full(b), 0, -2, hrow0 - 2, t, n);
+            }
+        }
+    } else if (warp == 1) {
+        if (elect_one() && my_tiles > 0) {
+            // D = f32, A = B = bf16, K-major, M = 128; N = 128 for X_hi x [W_hi ; W_lo], N = 64 for X_lo x W_hi
+            const uint32_t idesc_n = (1u << 4) | (1u << 7) | (1u << 10) | ((128u >> 4) << 24);
+            const uint32_t idesc2 = idesc_n | ((uint32_t)((2 * S2D_BN) >> 3) << 17);
+            const uint32_t idesc1 = idesc_n | ((uint32_t)(S2D_BN >> 3) << 17);
+            uint32_t sh2[S2D_TAPS];
+#pragma unroll
+            for (int t = 0; t < S2D_TAPS; ++t) sh2[t] = (uint32_t)hp.shift[t] * 2u;       // rows of 32 B in 16-byte units
+            const uint32_t patch16 = (uint32_t)hp.patch_bytes >> 4;
+            const uint32_t w_lo32 = (base >> 4) | 0x10000u;
+            mbar_wait(w_full, 0);
+            for (int i = 0; i < my_tiles; ++i) {
+                const int buf = i & 1;
+                const uint32_t td = tmem_base + (uint32_t)(buf * 2 * S2D_BN), tcx = td + (uint32_t)S2D_BN;
+                int n, t, f0, hrow0;
+                tile_origin(i, n, t, f0, hrow0);
+                const uint32_t a_lo32 = ((pbase + buf * pbuf + (uint32_t)(f0 - hrow0 * hp.PW) * 32u) >> 4) | 0x10000u;
+                mbar_wait(tm_empty(buf), (((uint32_t)i >> 1) & 1u) ^ 1u);
+                mbar_wait(p_full(buf), ((uint32_t)i >> 1) & 1u);
+                tc_fence_after();
+#pragma unroll
+                for (int tap = 0; tap < S2D_TAPS; ++tap) {
+                    const uint32_t ahi = a_lo32 + sh2[tap], alo = ahi + patch16, b = w_lo32 + (uint32_t)tap * (4096u >> 4);
+                    umma_bf16(td, S2D_DHI | (uint64_t)ahi, S2D_DHI | (uint64_t)b, idesc2, tap ? 1u : 0u);
+                    umma_bf16(tcx, S2D_DHI | (uint64_t)alo, S2D_DHI | (uint64_t)b, idesc1, 1u);
+                }
+                umma_commit(tm_full(buf));
+            }
+        }
+    } else {
+        // epilogue: 8 warps = 4 TMEM lane quarters (warp % 4) x two 32-column halves; BatchNorm partial sums stay in
+        // registers (one row per lane) across all tiles of the CTA and are transposed once at the end
+        const int q = warp & 3, c0 = ((warp - 2) >> 2) * 32;
+        float rs[32], rq[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) { rs[j] = 0.f; rq[j] = 0.f; }
+        for (int i = 0; i < my_tiles; ++i) {
+            const int buf = i & 1;
+            const uint32_t td = tmem_base + (uint32_t)(buf * 2 * S2D_BN), tcx = td + (uint32_t)S2D_BN;
+            int n, t, f0, hrow0;
+            tile_origin(i, n, t, f0, hrow0);
+            const int f = f0 + q * 32 + lane;
+            const int h = f / hp.PW, w = f - h * hp.PW;
+            const bool valid = h < hp.Ho && w < hp.Wo;
+            const long long row = (((long long)n * hp.T + t) * hp.Ho + h) * hp.Wo + w;
+            mbar_wait(tm_full(buf), ((uint32_t)i >> 1) & 1u);
+            tc_fence_after();
+            uint32_t v[32], u[32];
+            tmem_ld32_nowait(td + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+            tmem_ld32_nowait(tcx + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, u);
+            tmem_ld_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tm_empty(buf));
+            if (valid) {
+                float4* dst = reinterpret_cast<float4*>(y + row * S2D_BN + c0);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const float4 o = make_float4(__uint_as_float(v[4 * j]) + __uint_as_float(u[4 * j]),
+                                                 __uint_as_float(v[4 * j + 1]) + __uint_as_float(u[4 * j + 1]),
+                                                 __uint_as_float(v[4 * j + 2]) + __uint_as_float(u[4 * j + 2]),
+                                                 __uint_as_float(v[4 * j + 3]) + __uint_as_float(u[4 * j + 3]));
+                    if (stats) {
+                        rs[4 * j] += o.x; rs[4 * j + 1] += o.y; rs[4 * j + 2] += o.z; rs[4 * j + 3] += o.w;
+                        rq[4 * j] += o.x * o.x; rq[4 * j + 1] += o.y * o.y; rq[4 * j + 2] += o.z * o.z; rq[4 * j + 3] += o.w * o.w;
+                    }
+                    dst[j] = o;
+                }
+            }
+        }
+        if (stats) {
+            // lane l ends up with column c0 + l summed over the warp's 32 rows (31-shuffle transposing butterfly)
+#pragma unroll
+            for (int off = 16; off >= 1; off >>= 1) {
+                const bool up = (lane & off) != 0;
+#pragma unroll
+                for (int i = 0; i < off; ++i) {
+                    const float s_send = up ? rs[i] : rs[i + off], s_keep = up ? rs[i + off] : rs[i];
+                    const float q_send = up ? rq[i] : rq[i + off], q_keep = up ? rq[i + off] : rq[i];
+                    rs[i] = s_keep + __shfl_xor_sync(0xffffffffu, s_send, off);
+                    rq[i] = q_keep + __shfl_xor_sync(0xffffffffu, q_send, off);
+                }
+            }
+            atomicAdd(&stat_smem[c0 + lane], rs[0]);
+            atomicAdd(&stat_smem[64 + c0 + lane], rq[0]);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, tmem_cols);
+    if (stats && threadIdx.x < 128) atomicAdd(stats + threadIdx.x, (double)stat_smem[threadIdx.x]);
+}
+
+PFN_cuTensorMapEncodeTiled_v12000 s2d_encode() {
+    static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(p);
+    }
+    return fn;
+}
+
+}  // namespace
+
+// x [NB,3,T,H,W] fp32 -> split-bf16 space-to-depth planes x2_hi / x2_lo [NB,T,H/2,W/2,16]  (H, W even)
+extern "C" int dpc_stem_s2d_pack(const float* x, void* x2_hi, void* x2_lo, int NB, int T, int H, int W, void* stream) {
+    DPC_REQUIRE(x && x2_hi && x2_lo && NB > 0 && T > 0 && H > 0 && W > 0, "dpc_stem_s2d_pack: bad args");
+    DPC_REQUIRE((H & 1) == 0 && (W & 1) == 0, "dpc_stem_s2d_pack: H (%d) and W (%d) must be even", H, W);
+    const long long total = (long long)NB * T * (H / 2) * (W / 2);
+    const long long blocks = (total + 255) / 256, cap = (long long)dpc_num_sms() * 16;
+    stem_s2d_pack_kernel<<<(int)(blocks < cap ? blocks : cap), 256, 0, as_stream(stream)>>>(
+        x, reinterpret_cast<uint4*>(x2_hi), reinterpret_cast<uint4*>(x2_lo), NB, T, H, W);
+    DPC_LAUNCH_CHECK();
+    return DPC_OK;
+}
+
+// y [NB,T,H/2,W/2,64] = conv1(x) from the space-to-depth planes; `wp`: scratch of 32768 bf16 for the packed filter
+// bank; bn_ws (nullable): 128 doubles = per-channel sum | sum of squares of y
+extern "C" int dpc_stem_conv_fwd_s2d(const void* x2_hi, const void* x2_lo, const float* w, void* wp, float* y, double* bn_ws,
+                                     int NB, int T, int H, int W, void* stream) {
+    DPC_REQUIRE(x2_hi && x2_lo && w && wp && y && NB > 0 && T > 0 && H > 0 && W > 0, "dpc_stem_conv_fwd_s2d: bad args");
+    DPC_REQUIRE((H & 1) == 0 && (W & 1) == 0, "dpc_stem_conv_fwd_s2d: H (%d) and W (%d) must be even", H, W);
+    cudaStream_t st = as_stream(stream);
+    const int Ho = H / 2, Wo = W / 2;
+    S2dParams hp;
+    memset(&hp, 0, sizeof(hp));
+    hp.PW = Wo + 3;
+    hp.bhr = 4 + (130 + hp.PW - 1) / hp.PW;                   // rows [rowoff, rowoff + 128 + 3 * PW + 3), rowoff < PW
+    DPC_REQUIRE(hp.PW <= 256 && hp.bhr <= 256, "dpc_stem_conv_fwd_s2d: frame too wide (%d)", W);
+    hp.Ho = Ho; hp.Wo = Wo; hp.T = T;
+    hp.tiles_per_frame = (Ho * hp.PW + 127) / 128;
+    const long long total = (long long)NB * T * hp.tiles_per_frame;
+    DPC_REQUIRE(total < (1ll << 31), "dpc_stem_conv_fwd_s2d: too many tiles");
+    hp.total_tiles = (int)total;
+    hp.patch_bytes = ((hp.bhr * hp.PW * 32 + 1023) / 1024) * 1024;
+    for (int a = 0; a < 4; ++a)
+        for (int b = 0; b < 4; ++b) hp.shift[a * 4 + b] = a * hp.PW + b;
+    const size_t smem = S2D_W_BYTES + 4 * (size_t)hp.patch_bytes + 64 + 512 + 1024;
+    DPC_REQUIRE(smem <= 227 * 1024, "dpc_stem_conv_fwd_s2d: patch does not fit shared memory (W = %d)", W);
+    auto enc = s2d_encode();
+    DPC_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled entry point not available");
+    stem_s2d_wpack_kernel<<<(S2D_TAPS * S2D_BN * S2D_CH + 255) / 256, 256, 0, st>>>(w, reinterpret_cast<__nv_bfloat16*>(wp));
+    DPC_LAUNCH_CHECK();
+    S2dMaps maps;
+    {
+        const cuuint64_t gd[5] = {S2D_CH, (cuuint64_t)Wo, (cuuint64_t)Ho, (cuuint64_t)T, (cuuint64_t)NB};
+        const cuuint64_t gs[4] = {32, (cuuint64_t)Wo * 32, (cuuint64_t)Ho * Wo * 32, (cuuint64_t)T * Ho * Wo * 32};
+        const cuuint32_t bx[5] = {S2D_CH, (cuuint32_t)hp.PW, (cuuint32_t)hp.bhr, 1, 1}, es[5] = {1, 1, 1, 1, 1};
+        for (int i = 0; i < 2; ++i) {
+            CUresult r = enc(i ? &maps.x_lo : &maps.x_hi, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(i ? x2_lo : x2_hi),
+                             gd, gs, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_32B,
+                             CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            DPC_REQUIRE(r == CUDA_SUCCESS, "dpc_stem_conv_fwd_s2d: cuTensorMapEncodeTiled (x) failed (%d)", (int)r);
+        }
+        const cuuint64_t wd[2] = {S2D_CH, (cuuint64_t)S2D_TAPS * 2 * S2D_BN};
+        const cuuint64_t ws[1] = {32};
+        const cuuint32_t wb[2] = {S2D_CH, 256}, we[2] = {1, 1};
+        CUresult r = enc(&maps.w, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, wp, wd, ws, wb, we, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        DPC_REQUIRE(r == CUDA_SUCCESS, "dpc_stem_conv_fwd_s2d: cuTensorMapEncodeTiled (w) failed (%d)", (int)r);
+    }
+    if (bn_ws) DPC_CUDA(cudaMemsetAsync(bn_ws, 0, sizeof(double) * 128, st));
+    DPC_CUDA(cudaFuncSetAttribute(stem_s2d_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int sms = dpc_num_sms();
+    const int grid = hp.total_tiles < sms ? hp.total_tiles : sms;
+    stem_s2d_fwd_kernel<<<grid, 320, smem, st>>>(maps, hp, y, bn_ws);
+    DPC_LAUNCH_CHECK();
+    return DPC_OK;
+}

@@ -299,7 +299,17 @@ def backbone_forward(network, x, P, need_ctx=True, bn_state=None, training=True)
     y0 = _empty((rows0, 64), x)
     if USE_TC:
         ws0 = None if running else torch.empty(128, dtype=torch.float64, device=x.device)
-        _timed('stem_fwd')(L.stem_conv_fwd_tc)(ptr(x), ptr(P['conv1.weight']), ptr(y0), ptr(ws0), NB, T, H, W, st)
+        if H % 2 == 0 and W % 2 == 0:
+            # space-to-depth planes + TMA halo-patch kernel (stem_s2d.cu)
+            bf = dict(dtype=torch.bfloat16, device=x.device)
+            x2 = (torch.empty((NB, T, H // 2, W // 2, 16), **bf), torch.empty((NB, T, H // 2, W // 2, 16), **bf))
+            wp = torch.empty(32768, **bf)
+            _timed('stem_fwd')(L.stem_s2d_pack)(ptr(x), ptr(x2[0]), ptr(x2[1]), NB, T, H, W, st)
+            _timed('stem_fwd')(L.stem_conv_fwd_s2d)(ptr(x2[0]), ptr(x2[1]), ptr(P['conv1.weight']), ptr(wp), ptr(y0), ptr(ws0),
+                                                    NB, T, H, W, st)
+            del x2, wp
+        else:
+            _timed('stem_fwd')(L.stem_conv_fwd_tc)(ptr(x), ptr(P['conv1.weight']), ptr(y0), ptr(ws0), NB, T, H, W, st)
         if not running:
             m0, r0 = _empty((64,), x), _empty((64,), x)
             L.bn_finalize(ptr(ws0), rows0, 64, BN_EPS, ptr(m0), ptr(r0), st)

@@ -92,6 +92,13 @@ int dpc_stem_conv_fwd_tc(const float* x, const float* w, float* y, double* bn_ws
 /* dw [64,3,1,7,7] from the video and the split-bf16 planes of dy [NB,T,H/2,W/2,64] */
 int dpc_stem_conv_wgrad_tc(const float* x, const void* dy_hi, const void* dy_lo, float* dw, int NB, int T,
                            int H, int W, void* stream);
+/* Space-to-depth formulation of conv1 (same reference site): the stride-2 7x7 conv is a stride-1 4x4 conv over
+ * X2[h2,w2][(c,r,s)] = x[c,2*h2+r,2*w2+s], stored as split-bf16 planes [NB,T,H/2,W/2,16] (12 real channels).
+ * dpc_stem_s2d_pack builds the planes (H, W even); dpc_stem_conv_fwd_s2d computes y [NB,T,H/2,W/2,64] (+ bn1
+ * statistics in bn_ws, nullable) with TMA-fed tcgen05 MMAs; `wp` = scratch of 32768 bf16 for the packed filters. */
+int dpc_stem_s2d_pack(const float* x, void* x2_hi, void* x2_lo, int NB, int T, int H, int W, void* stream);
+int dpc_stem_conv_fwd_s2d(const void* x2_hi, const void* x2_lo, const float* w, void* wp, float* y, double* bn_ws,
+                          int NB, int T, int H, int W, void* stream);
 
 /* ---- BatchNorm3d(track_running_stats=False): batch statistics always ----------------------
  * replaces nn.BatchNorm3d at resnet_2d3d.py:55,59,91,95,212,243 (+ relu_ / `out += residual`

@@ -105,6 +105,25 @@ def test_stem_conv(NB, T, H, W):
     L.bn_finalize(ws.data_ptr(), y2.shape[0], 64, 1e-5, mean.data_ptr(), rstd.data_ptr(), _st())
     assert float((mean - y2.double().mean(0)).abs().max()) < 1e-5 * float(y2.abs().max())
     assert rel(rstd, 1 / torch.sqrt(y2.double().var(0, unbiased=False) + 1e-5)) < 1e-5
+    if H % 2 == 0 and W % 2 == 0:
+        # space-to-depth + TMA halo-patch version
+        bf = dict(dtype=torch.bfloat16, device='cuda')
+        x2h, x2l = torch.empty(NB, T, H // 2, W // 2, 16, **bf), torch.empty(NB, T, H // 2, W // 2, 16, **bf)
+        L.stem_s2d_pack(x.data_ptr(), x2h.data_ptr(), x2l.data_ptr(), NB, T, H, W, _st())
+        xs = x.view(NB, 3, T, H // 2, 2, W // 2, 2).permute(0, 2, 3, 5, 1, 4, 6).reshape(NB, T, H // 2, W // 2, 12)
+        assert torch.equal(x2h[..., :12], xs.to(torch.bfloat16)) and not x2h[..., 12:].any()
+        assert float(((x2h.float() + x2l.float())[..., :12] - xs).abs().max()) < 2.0 ** -15 * float(xs.abs().max())
+        y3 = torch.full_like(y, float('nan'))
+        ws3 = torch.empty(128, dtype=torch.float64, device='cuda')
+        wp = torch.empty(32768, **bf)
+        L.stem_conv_fwd_s2d(x2h.data_ptr(), x2l.data_ptr(), w.data_ptr(), wp.data_ptr(), y3.data_ptr(), ws3.data_ptr(),
+                            NB, T, H, W, _st())
+        torch.cuda.synchronize()
+        assert not torch.isnan(y3).any()
+        assert rel(from_rows(y3, NB, T, Ho, Wo), yref) < 5e-5
+        L.bn_finalize(ws3.data_ptr(), y3.shape[0], 64, 1e-5, mean.data_ptr(), rstd.data_ptr(), _st())
+        assert float((mean - y3.double().mean(0)).abs().max()) < 1e-5 * float(y3.abs().max())
+        assert rel(rstd, 1 / torch.sqrt(y3.double().var(0, unbiased=False) + 1e-5)) < 1e-5
     dy = torch.randn(yref.shape, device='cuda', generator=g)
     yref.backward(dy)
     dw = torch.empty_like(w)
