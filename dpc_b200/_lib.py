@@ -40,6 +40,7 @@ _SIGS = {
     'dpc_stem_conv_wgrad': (c_int, [P, P, P, c_int, c_int, c_int, c_int, P]),
     'dpc_stem_s2d_pack': (c_int, [P, P, P, c_int, c_int, c_int, c_int, P]),
     'dpc_stem_conv_fwd_s2d': (c_int, [P, P, P, P, P, P, c_int, c_int, c_int, c_int, P]),
+    'dpc_stem_conv_wgrad_s2d': (c_int, [P, P, P, P, P, c_int, c_int, c_int, c_int, P]),
     'dpc_bn_stats': (c_int, [P, c_int64, c_int, P, P, P, c_float, P]),
     'dpc_bn_finalize': (c_int, [P, c_int64, c_int, c_float, P, P, P]),
     'dpc_bn_apply_fwd': (c_int, [P, P, P, P, P, P, P, P, P, P, P, P, c_int, P, P, P, c_int64, c_int, P]),

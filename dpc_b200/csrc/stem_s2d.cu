@@ -237,6 +237,147 @@ stem_s2d_fwd_kernel(const __grid_constant__ S2dMaps maps, const S2dParams hp, fl
     if (stats && threadIdx.x < 128) atomicAdd(stats + threadIdx.x, (double)stat_smem[threadIdx.x]);
 }
 
+// =============================================================================================
+// wgrad of conv1 from the same planes:  dW2[co][(a,b)][ch] = sum_pos dY[pos, co] * X2[pos + (a-2, b-2)][ch]
+//
+// K = positions.  Tiles as in the forward; the dY rows of a tile come in one SWIZZLE_128B box whose out-of-frame
+// columns / rows are TMA zero fill, the X2 patch in one SWIZZLE_32B box.  Both operands are MN-major views:
+//   A (M = 128) = [dY_hi^T ; dY_lo^T]: the operand's two 64-channel groups are the two planes (LBO = plane pitch);
+//   B (N = 64)  = X2^T of the four taps (a, b = 0..3): four 16-channel groups one patch row (32 B) apart.
+// One instruction therefore yields dY_hi*X and dY_lo*X for four taps; issuing it for X_hi and X_lo gives all four
+// split products (rows 0-63: hi*hi + hi*lo, rows 64-127: lo*hi + lo*lo), which the drain adds.  4 accumulators of
+// 64 columns (one per a), flushed to dw with atomics every `chain` tiles.
+// =============================================================================================
+struct S2dWgMaps { CUtensorMap x_hi, x_lo, y_hi, y_lo; };
+
+struct S2dWgParams {
+    int PW, bhr_x, bhr_y, Ho, Wo, T;
+    int tiles_per_frame, total_tiles;
+    int xpatch_bytes, ypatch_bytes;
+    int chain;
+};
+
+__global__ void __launch_bounds__(192, 1)
+stem_s2d_wgrad_kernel(const __grid_constant__ S2dWgMaps maps, const S2dWgParams hp, float* __restrict__ dw) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // smem: 2 x [dy_hi | dy_lo | x_hi | x_lo] [barriers]
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t bufsz = 2u * (uint32_t)hp.ypatch_bytes + 2u * (uint32_t)hp.xpatch_bytes;
+    const uint32_t bar_base = base + 2u * bufsz;
+    auto full = [&](int b) { return bar_base + 8u * b; };
+    auto empty = [&](int b) { return bar_base + 8u * (2 + b); };
+    const uint32_t acc_full = bar_base + 32u, acc_empty = bar_base + 40u, tmem_ptr_addr = bar_base + 48u;
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.x_hi) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.x_lo) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.y_hi) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.y_lo) : "memory");
+        for (int b = 0; b < 2; ++b) { mbar_init(full(b), 1); mbar_init(empty(b), 1); }
+        mbar_init(acc_full, 1);
+        mbar_init(acc_empty, 4);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) tmem_alloc(tmem_ptr_addr, 256);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *reinterpret_cast<const uint32_t*>(smem_raw + (tmem_ptr_addr - smem_u32(smem_raw)));
+    const int my_tiles = ((int)blockIdx.x < hp.total_tiles) ? (hp.total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+    const int chains = (my_tiles + hp.chain - 1) / hp.chain;
+
+    auto tile_origin = [&](int i, int& n, int& t, int& f0, int& hrow0) {
+        const int tile = (int)blockIdx.x + i * (int)gridDim.x;
+        const int frame = tile / hp.tiles_per_frame;
+        f0 = (tile - frame * hp.tiles_per_frame) * 128;
+        hrow0 = f0 / hp.PW;
+        n = frame / hp.T; t = frame - n * hp.T;
+    };
+
+    if (warp == 0) {
+        if (elect_one()) {
+            const uint32_t tx = 2u * (uint32_t)(hp.bhr_x * hp.PW) * 32u + 2u * (uint32_t)(hp.bhr_y * hp.PW) * 128u;
+            for (int i = 0; i < my_tiles; ++i) {
+                const int b = i & 1;
+                int n, t, f0, hrow0;
+                tile_origin(i, n, t, f0, hrow0);
+                mbar_wait(empty(b), (((uint32_t)i >> 1) & 1u) ^ 1u);
+                mbar_expect_tx(full(b), tx);
+                const uint32_t sy = base + b * bufsz, sx = sy + 2u * hp.ypatch_bytes;
+                tma_load_5d(&maps.y_hi, sy, full(b), 0, 0, hrow0, t, n);
+                tma_load_5d(&maps.y_lo, sy + hp.ypatch_bytes, full(b), 0, 0, hrow0, t, n);
+                tma_load_5d(&maps.x_hi, sx, full(b), 0, -2, hrow0 - 2, t, n);
+                tma_load_5d(&maps.x_lo, sx + hp.xpatch_bytes, full(b), 0, -2, hrow0 - 2, t, n);
+            }
+        }
+    } else if (warp == 1) {
+        if (elect_one()) {
+            // D = f32, A = B = bf16, both MN-major (bits 15, 16), N = 64, M = 128
+            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((64u >> 3) << 17) | ((128u >> 4) << 24);
+            constexpr uint64_t DHI128 = 0x40004040ull << 32;   // SWIZZLE_128B, SBO = 1024 B
+            const uint32_t ylbo = ((uint32_t)hp.ypatch_bytes >> 4) << 16;      // A: dY_lo group = dY_hi group + one plane
+            const uint32_t xlbo = 2u << 16;                                    // B: next tap = next patch row (32 B)
+            const uint32_t xpatch16 = (uint32_t)hp.xpatch_bytes >> 4;
+            const uint32_t arow16 = (uint32_t)hp.PW * 2u;                      // one tap row a -> PW patch rows of 32 B
+            for (int i = 0; i < my_tiles; ++i) {
+                const int b = i & 1;
+                const int in_chain = i % hp.chain;
+                int n, t, f0, hrow0;
+                tile_origin(i, n, t, f0, hrow0);
+                const uint32_t rowoff = (uint32_t)(f0 - hrow0 * hp.PW);
+                const uint32_t y16 = (((base + b * bufsz) >> 4) + rowoff * 8u) | ylbo;
+                const uint32_t x16 = (((base + b * bufsz + 2u * hp.ypatch_bytes) >> 4) + rowoff * 2u) | xlbo;
+                if (in_chain == 0 && i > 0) mbar_wait(acc_empty, (((uint32_t)(i / hp.chain) - 1u) & 1u));
+                mbar_wait(full(b), ((uint32_t)i >> 1) & 1u);
+                tc_fence_after();
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {                  // UMMA_K = 16 positions: 2048 B of dY rows, 512 B of X2 rows
+                    const uint64_t ya = DHI128 | (uint64_t)(y16 + k * 128);
+#pragma unroll
+                    for (int a = 0; a < 4; ++a) {
+                        const uint32_t xa = x16 + (uint32_t)a * arow16 + k * 32;
+                        const uint32_t d = tmem_base + (uint32_t)(a * 64);
+                        umma_bf16(d, ya, S2D_DHI | (uint64_t)xa, idesc, (in_chain | k) ? 1u : 0u);
+                        umma_bf16(d, ya, S2D_DHI | (uint64_t)(xa + xpatch16), idesc, 1u);
+                    }
+                }
+                umma_commit(empty(b));
+                if (in_chain == hp.chain - 1 || i == my_tiles - 1) umma_commit(acc_full);
+            }
+        }
+    } else {
+        // drain: TMEM lane = (plane of dY, co); column = (b, ch) of tap row a
+        const int q = warp & 3;
+        const int co = (q * 32 + lane) & 63;
+        float* dwc = dw + (size_t)co * 147;
+        for (int c = 0; c < chains; ++c) {
+            mbar_wait(acc_full, (uint32_t)c & 1u);
+            tc_fence_after();
+#pragma unroll
+            for (int a = 0; a < 4; ++a) {
+                uint32_t v[32], u[32];
+                tmem_ld32_nowait(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * 64), v);
+                tmem_ld32_nowait(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * 64 + 32), u);
+                tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 64; ++j) {
+                    const int bb = j >> 4, ch = j & 15;
+                    const int cc = ch >> 2, r = (ch >> 1) & 1, s = ch & 1;
+                    const int kh = 2 * a + r - 1, kw = 2 * bb + s - 1;
+                    if (ch < 12 && kh >= 0 && kw >= 0)
+                        atomicAdd(dwc + cc * 49 + kh * 7 + kw, __uint_as_float(j < 32 ? v[j] : u[j - 32]));
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(acc_empty);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, 256);
+}
+
 PFN_cuTensorMapEncodeTiled_v12000 s2d_encode() {
     static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
     if (!fn) {
@@ -313,6 +454,65 @@ extern "C" int dpc_stem_conv_fwd_s2d(const void* x2_hi, const void* x2_lo, const
     const int sms = dpc_num_sms();
     const int grid = hp.total_tiles < sms ? hp.total_tiles : sms;
     stem_s2d_fwd_kernel<<<grid, 320, smem, st>>>(maps, hp, y, bn_ws);
+    DPC_LAUNCH_CHECK();
+    return DPC_OK;
+}
+
+// dw [64,3,1,7,7] = wgrad of conv1 from the space-to-depth planes and the split-bf16 planes of dy [NB,T,H/2,W/2,64]
+extern "C" int dpc_stem_conv_wgrad_s2d(const void* x2_hi, const void* x2_lo, const void* dy_hi, const void* dy_lo, float* dw,
+                                       int NB, int T, int H, int W, void* stream) {
+    DPC_REQUIRE(x2_hi && x2_lo && dy_hi && dy_lo && dw && NB > 0 && T > 0 && H > 0 && W > 0, "dpc_stem_conv_wgrad_s2d: bad args");
+    DPC_REQUIRE((H & 1) == 0 && (W & 1) == 0, "dpc_stem_conv_wgrad_s2d: H (%d) and W (%d) must be even", H, W);
+    cudaStream_t st = as_stream(stream);
+    const int Ho = H / 2, Wo = W / 2;
+    S2dWgParams hp;
+    memset(&hp, 0, sizeof(hp));
+    hp.PW = Wo + 3;
+    hp.bhr_x = 4 + (130 + hp.PW - 1) / hp.PW;
+    hp.bhr_y = (127 + 2 * hp.PW - 1) / hp.PW;
+    DPC_REQUIRE(hp.PW <= 256 && hp.bhr_x <= 256, "dpc_stem_conv_wgrad_s2d: frame too wide (%d)", W);
+    hp.Ho = Ho; hp.Wo = Wo; hp.T = T;
+    hp.tiles_per_frame = (Ho * hp.PW + 127) / 128;
+    const long long total = (long long)NB * T * hp.tiles_per_frame;
+    DPC_REQUIRE(total < (1ll << 31), "dpc_stem_conv_wgrad_s2d: too many tiles");
+    hp.total_tiles = (int)total;
+    hp.xpatch_bytes = ((hp.bhr_x * hp.PW * 32 + 1023) / 1024) * 1024;
+    hp.ypatch_bytes = ((hp.bhr_y * hp.PW * 128 + 1023) / 1024) * 1024;
+    hp.chain = 64;              // 64 tiles x 8 k-steps x 2 products: 1024 truncating accumulations per TMEM chain
+    const size_t smem = 2 * (2 * (size_t)hp.xpatch_bytes + 2 * (size_t)hp.ypatch_bytes) + 64 + 1024;
+    DPC_REQUIRE(smem <= 227 * 1024, "dpc_stem_conv_wgrad_s2d: patches do not fit shared memory (W = %d)", W);
+    DPC_REQUIRE((hp.ypatch_bytes >> 4) < (1 << 14), "dpc_stem_conv_wgrad_s2d: plane pitch exceeds the descriptor LBO field");
+    auto enc = s2d_encode();
+    DPC_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled entry point not available");
+    S2dWgMaps maps;
+    const cuuint32_t es[5] = {1, 1, 1, 1, 1};
+    {
+        const cuuint64_t gd[5] = {S2D_CH, (cuuint64_t)Wo, (cuuint64_t)Ho, (cuuint64_t)T, (cuuint64_t)NB};
+        const cuuint64_t gs[4] = {32, (cuuint64_t)Wo * 32, (cuuint64_t)Ho * Wo * 32, (cuuint64_t)T * Ho * Wo * 32};
+        const cuuint32_t bx[5] = {S2D_CH, (cuuint32_t)hp.PW, (cuuint32_t)hp.bhr_x, 1, 1};
+        for (int i = 0; i < 2; ++i) {
+            CUresult r = enc(i ? &maps.x_lo : &maps.x_hi, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(i ? x2_lo : x2_hi),
+                             gd, gs, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_32B,
+                             CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            DPC_REQUIRE(r == CUDA_SUCCESS, "dpc_stem_conv_wgrad_s2d: cuTensorMapEncodeTiled (x) failed (%d)", (int)r);
+        }
+    }
+    {
+        const cuuint64_t gd[5] = {64, (cuuint64_t)Wo, (cuuint64_t)Ho, (cuuint64_t)T, (cuuint64_t)NB};
+        const cuuint64_t gs[4] = {128, (cuuint64_t)Wo * 128, (cuuint64_t)Ho * Wo * 128, (cuuint64_t)T * Ho * Wo * 128};
+        const cuuint32_t bx[5] = {64, (cuuint32_t)hp.PW, (cuuint32_t)hp.bhr_y, 1, 1};
+        for (int i = 0; i < 2; ++i) {
+            CUresult r = enc(i ? &maps.y_lo : &maps.y_hi, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(i ? dy_lo : dy_hi),
+                             gd, gs, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                             CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            DPC_REQUIRE(r == CUDA_SUCCESS, "dpc_stem_conv_wgrad_s2d: cuTensorMapEncodeTiled (dy) failed (%d)", (int)r);
+        }
+    }
+    DPC_CUDA(cudaMemsetAsync(dw, 0, sizeof(float) * 64 * 147, st));
+    DPC_CUDA(cudaFuncSetAttribute(stem_s2d_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int sms = dpc_num_sms();
+    const int grid = hp.total_tiles < sms ? hp.total_tiles : sms;
+    stem_s2d_wgrad_kernel<<<grid, 192, smem, st>>>(maps, hp, dw);
     DPC_LAUNCH_CHECK();
     return DPC_OK;
 }

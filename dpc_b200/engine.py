@@ -297,6 +297,7 @@ def backbone_forward(network, x, P, need_ctx=True, bn_state=None, training=True)
     Ho, Wo = _out_extent(H, 7, 2, 3), _out_extent(W, 7, 2, 3)
     rows0 = NB * T * Ho * Wo
     y0 = _empty((rows0, 64), x)
+    x2 = None
     if USE_TC:
         ws0 = None if running else torch.empty(128, dtype=torch.float64, device=x.device)
         if H % 2 == 0 and W % 2 == 0:
@@ -307,8 +308,9 @@ def backbone_forward(network, x, P, need_ctx=True, bn_state=None, training=True)
             _timed('stem_fwd')(L.stem_s2d_pack)(ptr(x), ptr(x2[0]), ptr(x2[1]), NB, T, H, W, st)
             _timed('stem_fwd')(L.stem_conv_fwd_s2d)(ptr(x2[0]), ptr(x2[1]), ptr(P['conv1.weight']), ptr(wp), ptr(y0), ptr(ws0),
                                                     NB, T, H, W, st)
-            del x2, wp
+            del wp
         else:
+            x2 = None
             _timed('stem_fwd')(L.stem_conv_fwd_tc)(ptr(x), ptr(P['conv1.weight']), ptr(y0), ptr(ws0), NB, T, H, W, st)
         if not running:
             m0, r0 = _empty((64,), x), _empty((64,), x)
@@ -327,7 +329,7 @@ def backbone_forward(network, x, P, need_ctx=True, bn_state=None, training=True)
     a0 = _empty((NB * T * Hp * Wp, 64), x)
     _timed('stem_pool_fwd')(L.bn_relu_maxpool_fwd)(ptr(y0), ptr(m0), ptr(r0), ptr(P['bn1.weight']), ptr(P['bn1.bias']), ptr(a0),
                           NB * T, Ho, Wo, 64, st)
-    ctx = dict(network=network, x=x, y0=y0, m0=m0, r0=r0, a0=a0, stem_dims=(NB, T, H, W, Ho, Wo), blocks=[])
+    ctx = dict(network=network, x=x, x2=x2, y0=y0, m0=m0, r0=r0, a0=a0, stem_dims=(NB, T, H, W, Ho, Wo), blocks=[])
     cur, dims, C = a0, (T, Hp, Wp), 64
     tc = USE_TC
     Site = TcConvSite if tc else ConvSite
@@ -491,7 +493,10 @@ def _backbone_backward(ctx, dout, P, side):
                                              ptr(dy0p[1]), NB * T, Ho, Wo, 64, 1, st)
     del dout
     dw0 = torch.empty_like(P['conv1.weight'])
-    if tc:
+    if tc and ctx.get('x2') is not None:
+        x2 = ctx['x2']
+        _timed('stem_wgrad')(L.stem_conv_wgrad_s2d)(ptr(x2[0]), ptr(x2[1]), ptr(dy0p[0]), ptr(dy0p[1]), ptr(dw0), NB, T, H, W, st)
+    elif tc:
         _timed('stem_wgrad')(L.stem_conv_wgrad_tc)(ptr(ctx['x']), ptr(dy0p[0]), ptr(dy0p[1]), ptr(dw0), NB, T, H, W, st)
     else:
         _timed('stem_wgrad')(L.stem_conv_wgrad)(ptr(ctx['x']), ptr(dy0), ptr(dw0), NB, T, H, W, st)

@@ -99,6 +99,9 @@ int dpc_stem_conv_wgrad_tc(const float* x, const void* dy_hi, const void* dy_lo,
 int dpc_stem_s2d_pack(const float* x, void* x2_hi, void* x2_lo, int NB, int T, int H, int W, void* stream);
 int dpc_stem_conv_fwd_s2d(const void* x2_hi, const void* x2_lo, const float* w, void* wp, float* y, double* bn_ws,
                           int NB, int T, int H, int W, void* stream);
+/* dw [64,3,1,7,7] from the space-to-depth planes and the split-bf16 planes of dy [NB,T,H/2,W/2,64] */
+int dpc_stem_conv_wgrad_s2d(const void* x2_hi, const void* x2_lo, const void* dy_hi, const void* dy_lo, float* dw,
+                            int NB, int T, int H, int W, void* stream);
 
 /* ---- BatchNorm3d(track_running_stats=False): batch statistics always ----------------------
  * replaces nn.BatchNorm3d at resnet_2d3d.py:55,59,91,95,212,243 (+ relu_ / `out += residual`

@@ -136,6 +136,13 @@ def test_stem_conv(NB, T, H, W):
     torch.cuda.synchronize()
     assert not torch.isnan(dw2).any()
     assert rel(dw2, wr.grad) < 5e-5
+    if H % 2 == 0 and W % 2 == 0:
+        dw3 = torch.full_like(w, float('nan'))
+        L.stem_conv_wgrad_s2d(x2h.data_ptr(), x2l.data_ptr(), dyp[0].data_ptr(), dyp[1].data_ptr(), dw3.data_ptr(),
+                              NB, T, H, W, _st())
+        torch.cuda.synchronize()
+        assert not torch.isnan(dw3).any()
+        assert rel(dw3, wr.grad) < 5e-5
 
 
 @pytest.mark.parametrize('C,rows', [(64, 5000), (128, 1237), (256, 96)])
