@@ -480,7 +480,7 @@ __device__ __forceinline__ void halo_issue_tile(uint32_t a_lo, const uint32_t (&
             umma_bf16(td, DHI | (uint64_t)(ahi + 2 * k), DHI | (uint64_t)(b + 2 * k), idesc2, (t | k) ? 1u : 0u);
             umma_bf16(tcx, DHI | (uint64_t)(alo + 2 * k), DHI | (uint64_t)(b + 2 * k), idesc1, 1u);
         }
-        if (s & 1) umma_commit(bempty0 + 8u * (s >> 1));            // releases stages s-1 and s
+        if (s & 1) umma_commit(bempty0 + 8u * (s >> 1));            // releases stages s-1 and s (triples measured slower)
         if (s == HALO_STAGES - 1) ph ^= 1u;
     }
     umma_commit(tmfull);

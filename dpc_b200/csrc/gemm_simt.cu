@@ -77,6 +77,74 @@ __global__ void __launch_bounds__(256) gemm_f32_kernel(int M, int N, int K, floa
     }
 }
 
+// Full-tile fast path (M % 64 == N % 64 == 0, K slice % 16 == 0, 16-byte aligned operands): one float4 global load
+// per thread and operand per k-tile, issued one k-tile ahead of the FMAs (register prefetch), so the global latency
+// of the small latency-bound head GEMMs (2048 x 256 x 256) overlaps the math.
+template <bool TA, bool TB, bool SPLITK>
+__global__ void __launch_bounds__(256) gemm_f32_vec_kernel(int M, int N, int K, float alpha,
+                                                            const float* __restrict__ A, int lda,
+                                                            const float* __restrict__ B, int ldb,
+                                                            float beta, float* __restrict__ C, int ldc, int kslice) {
+    __shared__ __align__(16) float As[TK][TM + 4];
+    __shared__ __align__(16) float Bs[TK][TN + 4];
+    const int tid = threadIdx.x;
+    const int m0 = blockIdx.y * TM, n0 = blockIdx.x * TN;
+    const int tm = (tid / 16) * 4, tn = (tid % 16) * 4;
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    const int kbeg = SPLITK ? blockIdx.z * kslice : 0;
+    const int kend = SPLITK ? (kbeg + kslice < K ? kbeg + kslice : K) : K;
+    // this thread's float4 of the A / B k-tile
+    const int am = TA ? (tid % 16) * 4 : tid / 4, ak = TA ? tid / 16 : (tid % 4) * 4;
+    const int bn = TB ? tid / 4 : (tid % 16) * 4, bk = TB ? (tid % 4) * 4 : tid / 16;
+    auto lda4 = [&](int k0) {
+        return TA ? *reinterpret_cast<const float4*>(A + (size_t)(k0 + ak) * lda + m0 + am)
+                  : *reinterpret_cast<const float4*>(A + (size_t)(m0 + am) * lda + k0 + ak);
+    };
+    auto ldb4 = [&](int k0) {
+        return TB ? *reinterpret_cast<const float4*>(B + (size_t)(n0 + bn) * ldb + k0 + bk)
+                  : *reinterpret_cast<const float4*>(B + (size_t)(k0 + bk) * ldb + n0 + bn);
+    };
+    float4 pa = lda4(kbeg), pb = ldb4(kbeg);
+    for (int k0 = kbeg; k0 < kend; k0 += TK) {
+        if (TA) *reinterpret_cast<float4*>(&As[ak][am]) = pa;
+        else { As[ak][am] = pa.x; As[ak + 1][am] = pa.y; As[ak + 2][am] = pa.z; As[ak + 3][am] = pa.w; }
+        if (TB) { Bs[bk][bn] = pb.x; Bs[bk + 1][bn] = pb.y; Bs[bk + 2][bn] = pb.z; Bs[bk + 3][bn] = pb.w; }
+        else *reinterpret_cast<float4*>(&Bs[bk][bn]) = pb;
+        __syncthreads();
+        if (k0 + TK < kend) { pa = lda4(k0 + TK); pb = ldb4(k0 + TK); }
+#pragma unroll
+        for (int k = 0; k < TK; ++k) {
+            const float4 a = *reinterpret_cast<const float4*>(&As[k][tm]);
+            const float4 b = *reinterpret_cast<const float4*>(&Bs[k][tn]);
+            const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        float* c = &C[(size_t)(m0 + tm + i) * ldc + n0 + tn];
+        if (SPLITK) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) atomicAdd(c + j, alpha * acc[i][j]);
+        } else {
+            float4 v = make_float4(alpha * acc[i][0], alpha * acc[i][1], alpha * acc[i][2], alpha * acc[i][3]);
+            if (beta != 0.f) {
+                const float4 o = *reinterpret_cast<const float4*>(c);
+                v.x += beta * o.x; v.y += beta * o.y; v.z += beta * o.z; v.w += beta * o.w;
+            }
+            *reinterpret_cast<float4*>(c) = v;
+        }
+    }
+}
+
 __global__ void scale_matrix_kernel(float* __restrict__ C, int M, int N, int ldc, float beta) {
     long long total = (long long)M * N;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -116,22 +184,25 @@ __global__ void scatter_rows_kernel(const float4* __restrict__ src, float4* __re
     }
 }
 
-// colsum: grid.x over column groups of 32, each block reduces all rows for 32 columns.
+// colsum: grid.x over column groups of 32, grid.y over row chunks; partial sums are added with atomics
+// (`out` is zeroed by the launcher unless it accumulates)
 __global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ A, long long rows, int N,
-                                                      float* __restrict__ out, int accumulate) {
+                                                      float* __restrict__ out, long long chunk) {
     __shared__ float red[8][33];
     int col = blockIdx.x * 32 + (threadIdx.x & 31);
     int rl = threadIdx.x >> 5;
+    const long long r0 = (long long)blockIdx.y * chunk;
+    const long long r1 = r0 + chunk < rows ? r0 + chunk : rows;
     float s = 0.f;
     if (col < N)
-        for (long long r = rl; r < rows; r += 8) s += A[r * N + col];
+        for (long long r = r0 + rl; r < r1; r += 8) s += A[r * N + col];
     red[rl][threadIdx.x & 31] = s;
     __syncthreads();
     if (rl == 0 && col < N) {
         float t = 0.f;
 #pragma unroll
         for (int i = 0; i < 8; ++i) t += red[i][threadIdx.x & 31];
-        out[col] = accumulate ? out[col] + t : t;
+        atomicAdd(out + col, t);
     }
 }
 
@@ -153,6 +224,8 @@ extern "C" int dpc_gemm_f32(int transA, int transB, int M, int N, int K, float a
         if (splits > K / 128) splits = K / 128;
         if (splits < 1) splits = 1;
     }
+    const bool vec = M % TM == 0 && N % TN == 0 && K % TK == 0 && lda % 4 == 0 && ldb % 4 == 0 && ldc % 4 == 0 &&
+                     ((uintptr_t)A & 15) == 0 && ((uintptr_t)B & 15) == 0 && ((uintptr_t)C & 15) == 0;
     if (splits > 1) {
         int kslice = ((K + splits - 1) / splits + TK - 1) / TK * TK;
         splits = (K + kslice - 1) / kslice;
@@ -161,7 +234,11 @@ extern "C" int dpc_gemm_f32(int transA, int transB, int M, int N, int K, float a
             DPC_LAUNCH_CHECK();
         }
         grid.z = splits;
-#define GEMM_SK(TA_, TB_) gemm_f32_kernel<TA_, TB_, true><<<grid, 256, 0, st>>>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, kslice)
+#define GEMM_SK(TA_, TB_)                                                                                              \
+    do {                                                                                                               \
+        if (vec) gemm_f32_vec_kernel<TA_, TB_, true><<<grid, 256, 0, st>>>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, kslice); \
+        else gemm_f32_kernel<TA_, TB_, true><<<grid, 256, 0, st>>>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, kslice);         \
+    } while (0)
         if (!transA && !transB) GEMM_SK(false, false);
         else if (!transA && transB) GEMM_SK(false, true);
         else if (transA && !transB) GEMM_SK(true, false);
@@ -170,7 +247,11 @@ extern "C" int dpc_gemm_f32(int transA, int transB, int M, int N, int K, float a
         DPC_LAUNCH_CHECK();
         return DPC_OK;
     }
-#define GEMM_1(TA_, TB_) gemm_f32_kernel<TA_, TB_, false><<<grid, 256, 0, st>>>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, K)
+#define GEMM_1(TA_, TB_)                                                                                               \
+    do {                                                                                                               \
+        if (vec) gemm_f32_vec_kernel<TA_, TB_, false><<<grid, 256, 0, st>>>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, K); \
+        else gemm_f32_kernel<TA_, TB_, false><<<grid, 256, 0, st>>>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, K);         \
+    } while (0)
     if (!transA && !transB) GEMM_1(false, false);
     else if (!transA && transB) GEMM_1(false, true);
     else if (transA && !transB) GEMM_1(true, false);
@@ -206,7 +287,13 @@ extern "C" int dpc_scatter_rows(const float* src, float* dst, int64_t rows, int 
 
 extern "C" int dpc_colsum(const float* A, int64_t rows, int N, float* out, int accumulate, void* stream) {
     DPC_REQUIRE(rows > 0 && N > 0, "dpc_colsum: bad args");
-    colsum_kernel<<<ceil_div(N, 32), 256, 0, as_stream(stream)>>>(A, rows, N, out, accumulate);
+    if (!accumulate) DPC_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * (size_t)N, as_stream(stream)));
+    long long chunks = (rows + 127) / 128;                       // >= 128 rows per block
+    const long long cap = (2ll * dpc_num_sms() + ceil_div(N, 32) - 1) / ceil_div(N, 32);
+    if (chunks > cap) chunks = cap;
+    if (chunks < 1) chunks = 1;
+    const long long chunk = (rows + chunks - 1) / chunks;
+    colsum_kernel<<<dim3(ceil_div(N, 32), (unsigned)((rows + chunk - 1) / chunk)), 256, 0, as_stream(stream)>>>(A, rows, N, out, chunk);
     DPC_LAUNCH_CHECK();
     return DPC_OK;
 }

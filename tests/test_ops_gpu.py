@@ -286,7 +286,8 @@ def test_pool_split():
 
 
 @pytest.mark.parametrize('ta,tb', [(0, 0), (0, 1), (1, 0), (1, 1)])
-@pytest.mark.parametrize('M,N,K', [(200, 256, 512), (96, 96, 256), (33, 70, 19)])
+@pytest.mark.parametrize('M,N,K', [(200, 256, 512), (96, 96, 256), (33, 70, 19), (2048, 256, 256), (256, 256, 2048),
+                                   (128, 512, 64)])
 def test_gemm_f32(ta, tb, M, N, K):
     L = _lib()
     g = torch.Generator(device='cuda').manual_seed(6)
