@@ -33,6 +33,7 @@ _SIGS = {
     'dpc_gemm_nt_bf16x3_tc': (c_int, [c_int, c_int, c_int, P, P, P, P, P, c_int, P]),
     'dpc_conv3d_fwd_tc': (c_int, [POINTER(ConvGeom), P, P, P, P, P, P, P]),
     'dpc_conv3d_dgrad_tc': (c_int, [POINTER(ConvGeom), P, P, P, P, P, c_int, P]),
+    'dpc_conv3d_dgrad_bnred_tc': (c_int, [POINTER(ConvGeom), P, P, P, P, P, c_int, P, P, P, P, P, P]),
     'dpc_conv3d_wgrad_tc': (c_int, [POINTER(ConvGeom), P, P, P, P, P, P, P]),
     'dpc_stem_conv_fwd': (c_int, [P, P, P, c_int, c_int, c_int, c_int, P]),
     'dpc_stem_conv_fwd_tc': (c_int, [P, P, P, P, c_int, c_int, c_int, c_int, P]),
@@ -45,6 +46,7 @@ _SIGS = {
     'dpc_bn_finalize': (c_int, [P, c_int64, c_int, c_float, P, P, P]),
     'dpc_bn_apply_fwd': (c_int, [P, P, P, P, P, P, P, P, P, P, P, P, c_int, P, P, P, c_int64, c_int, P]),
     'dpc_bn_bwd': (c_int, [P, P, P, c_int, P, P, P, P, P, P, P, P, P, P, P, c_int64, c_int, P]),
+    'dpc_bn_bwd_apply': (c_int, [P, P, P, c_int, P, P, P, P, P, P, P, P, P, P, P, c_int64, c_int, P]),
     'dpc_bn_relu_maxpool_fwd': (c_int, [P, P, P, P, P, P, c_int, c_int, c_int, c_int, P]),
     'dpc_bn_relu_maxpool_bwd': (c_int, [P, P, P, P, P, P, P, P, c_int, c_int, c_int, c_int, P]),
     'dpc_stem_tail_bwd': (c_int, [P, P, P, P, P, P, P, P, P, P, P, P, P, c_int, c_int, c_int, c_int, c_int, P]),

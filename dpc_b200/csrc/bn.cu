@@ -597,6 +597,28 @@ extern "C" int dpc_bn_bwd(const float* dout, const float* out, const void* out_h
     return DPC_OK;
 }
 
+// BatchNorm backward when the reduction already exists (ws = [sum g | sum g*xhat] doubles, e.g. produced by
+// dpc_conv3d_dgrad_bnred_tc's epilogue): dgamma / dbeta from ws, then the apply pass only.
+extern "C" int dpc_bn_bwd_apply(const float* dout, const float* out, const void* out_hi, int relu, const float* y,
+                                const float* mean, const float* rstd, const float* gamma, const double* ws,
+                                float* dgamma, float* dbeta, float* dy, void* dy_hi, void* dy_lo, float* g_out,
+                                int64_t rows, int C, void* stream) {
+    DPC_REQUIRE(dout && y && mean && rstd && gamma && ws && dgamma && dbeta && rows > 0, "dpc_bn_bwd_apply: bad args");
+    DPC_REQUIRE(dy || (dy_hi && dy_lo), "dpc_bn_bwd_apply: no output");
+    DPC_REQUIRE(!dy_hi == !dy_lo, "dpc_bn_bwd_apply: planes come in pairs");
+    DPC_REQUIRE(!relu || out || out_hi, "dpc_bn_bwd_apply: relu needs the forward output (rows or hi plane)");
+    if (int rc = check_c(C, "dpc_bn_bwd_apply")) return rc;
+    cudaStream_t st = as_stream(stream);
+    const int C4 = C / 4, rg = THREADS / C4;
+    bn_bwd_finalize_kernel<<<ceil_div(C, 128), 128, 0, st>>>(ws, C, dgamma, dbeta);
+    DPC_LAUNCH_CHECK();
+    bn_bwd_apply_kernel<<<stream_grid(rows, rg), THREADS, 0, st>>>(dout, out, out_hi, relu, y, mean, rstd, gamma, ws,
+                                                                   dy, dy_hi, dy_lo, g_out, rows, C);
+    DPC_LAUNCH_CHECK();
+    return DPC_OK;
+}
+
+
 extern "C" int dpc_bn_relu_maxpool_fwd(const float* y, const float* mean, const float* rstd, const float* gamma,
                                        const float* beta, float* out, int NT, int H, int W, int C, void* stream) {
     DPC_REQUIRE(y && mean && rstd && gamma && beta && out && NT > 0 && H > 0 && W > 0, "dpc_bn_relu_maxpool_fwd: bad args");

@@ -35,7 +35,22 @@ struct TcMaps {
     CUtensorMap b_hi, b_lo;           // second operand
 };
 
+// Optional fused reduction of the epilogue (sums over output rows per output channel, written to `stats` as
+// [sum_a (Co) | sum_b (Co)] doubles):
+//   y == nullptr: BatchNorm batch statistics of the conv output v:      a = v,  b = v^2           (forward)
+//   y != nullptr: BatchNorm-BACKWARD sums of the BN that produced the conv's INPUT gradient target, i.e. with
+//                 g = v * [mask_hi > 0] (ReLU mask of that BN's output; nullptr = no ReLU) and
+//                 xhat = (y - mean) * rstd (that BN's input):            a = g,  b = g * xhat      (dgrad)
+// so bn_bwd's separate reduce pass over dgrad's output disappears (bn.cu: dpc_bn_bwd_apply consumes the sums).
+struct BnRed {
+    const __nv_bfloat16* mask_hi;
+    const float* y;
+    const float* mean;
+    const float* rstd;
+};
+
 struct TcParams {
+    BnRed red;
     TapDim tT, tH, tW;
     int kH, kW;                // full filter extents (to linearise the original tap index)
     int sH, sW;                // strides (to linearise the parity-view index)
@@ -130,7 +145,11 @@ __device__ __forceinline__ void tile_epilogue_rows(const TcParams& p, float* __r
                     float4 o = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
                                            __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
                     float4* dst = reinterpret_cast<float4*>(yrow + c0) + j;
-                    if (accumulate) { float4 c = *dst; o.x += c.x; o.y += c.y; o.z += c.z; o.w += c.w; }
+                    if (accumulate) {
+                        float4 c = *dst; o.x += c.x; o.y += c.y; o.z += c.z; o.w += c.w;
+                        v[4 * j] = __float_as_uint(o.x); v[4 * j + 1] = __float_as_uint(o.y);
+                        v[4 * j + 2] = __float_as_uint(o.z); v[4 * j + 3] = __float_as_uint(o.w);
+                    }
                     *dst = o;
                 }
             } else {
@@ -138,7 +157,7 @@ __device__ __forceinline__ void tile_epilogue_rows(const TcParams& p, float* __r
                 for (int j = 0; j < 32; ++j) {
                     if (ncol0 + c0 + j < p.Co) {
                         float o = __uint_as_float(v[j]);
-                        if (accumulate) o += yrow[c0 + j];
+                        if (accumulate) { o += yrow[c0 + j]; v[j] = __float_as_uint(o); }
                         yrow[c0 + j] = o;
                     }
                 }
@@ -149,10 +168,39 @@ __device__ __forceinline__ void tile_epilogue_rows(const TcParams& p, float* __r
             // over the warp's 32 rows by a 31-shuffle transposing butterfly (lane l ends up with column
             // c0+l), then shared-memory partials per CTA.
             float sv[32], sq[32];
+            if (p.red.y) {
+                // BatchNorm-backward sums (see BnRed): g = v * [mask > 0], b = g * (y - mean) * rstd; mean / rstd of
+                // this CTA's columns sit in shared memory behind the partial sums
+                const bool full = valid && ncol0 + c0 + 32 <= p.Co && (p.Co & 7) == 0;
+                const size_t off = (size_t)(valid ? row : 0) * p.Co + ncol0 + c0;
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-                const float f = valid ? __uint_as_float(v[j]) : 0.f;
-                sv[j] = f; sq[j] = f * f;
+                for (int j8 = 0; j8 < 4; ++j8) {
+                    uint4 mk = make_uint4(0x3f803f80u, 0x3f803f80u, 0x3f803f80u, 0x3f803f80u);      // +1: keep
+                    float4 ya = make_float4(0.f, 0.f, 0.f, 0.f), yb = ya;
+                    if (full) {
+                        if (p.red.mask_hi) mk = *reinterpret_cast<const uint4*>(p.red.mask_hi + off + 8 * j8);
+                        ya = *reinterpret_cast<const float4*>(p.red.y + off + 8 * j8);
+                        yb = *reinterpret_cast<const float4*>(p.red.y + off + 8 * j8 + 4);
+                    }
+                    const uint32_t mw[4] = {mk.x, mk.y, mk.z, mk.w};
+                    const float yv[8] = {ya.x, ya.y, ya.z, ya.w, yb.x, yb.y, yb.z, yb.w};
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) {
+                        const int j = 8 * j8 + e;
+                        // bf16 > 0  <=>  sign bit clear and not zero
+                        const uint32_t hb = (e & 1) ? (mw[e >> 1] >> 16) : (mw[e >> 1] & 0xffffu);
+                        const bool keep = full && (hb & 0x8000u) == 0u && (hb & 0x7fffu) != 0u;
+                        const float gv = keep ? __uint_as_float(v[j]) : 0.f;
+                        sv[j] = gv;
+                        sq[j] = gv * (yv[e] - stat_smem[512 + c0 + j]) * stat_smem[768 + c0 + j];
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const float f = valid ? __uint_as_float(v[j]) : 0.f;
+                    sv[j] = f; sq[j] = f * f;
+                }
             }
 #pragma unroll
             for (int off = 16; off >= 1; off >>= 1) {
@@ -182,8 +230,15 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p, float* __r
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     // per-CTA BatchNorm partials (sum | sum of squares), after the barrier block
     float* stat_smem = reinterpret_cast<float*>(smem_raw + (sp.bar_base + 8u * (2 * p.stages + 2) - smem_u32(smem_raw)));
-    if (stats)
+    if (stats) {
         for (int i = threadIdx.x; i < 512; i += blockDim.x) stat_smem[i] = 0.f;
+        if (p.red.y)
+            for (int c = threadIdx.x; c < p.BN; c += blockDim.x) {
+                const int col = blockIdx.y * p.BN + c;
+                stat_smem[512 + c] = col < p.Co ? p.red.mean[col] : 0.f;
+                stat_smem[768 + c] = col < p.Co ? p.red.rstd[col] : 0.f;
+            }
+    }
     // Two accumulators: columns [0,BN) take hi*hi, [BN,2BN) the two cross terms.  The TMEM accumulate
     // truncates (measured: mean relative error -2e-8 per accumulation step), so keeping the small terms
     // out of the main chain cuts that bias 3x; the epilogue adds the two in fp32 (round-to-nearest).
@@ -304,8 +359,14 @@ conv_tc_persist_kernel(const __grid_constant__ TcMaps maps, const TcParams p, fl
     auto tm_empty = [&](int b) { return bar_base + 8u * (2 * p.stages + 3 + b); };
     const uint32_t tmem_ptr_addr = bar_base + 8u * (2 * p.stages + 5);
     float* stat_smem = reinterpret_cast<float*>(smem_raw + (bar_base + 8u * (2 * p.stages + 6) - smem_u32(smem_raw)));
-    if (stats)
+    if (stats) {
         for (int i = threadIdx.x; i < 512; i += blockDim.x) stat_smem[i] = 0.f;
+        if (p.red.y)
+            for (int c = threadIdx.x; c < p.BN; c += blockDim.x) {
+                stat_smem[512 + c] = c < p.Co ? p.red.mean[c] : 0.f;
+                stat_smem[768 + c] = c < p.Co ? p.red.rstd[c] : 0.f;
+            }
+    }
     const uint32_t tmem_cols = 4u * (uint32_t)p.BN;            // 2 buffers x (main + cross-term) accumulators
     if (warp == 0 && lane == 0) {
         for (int v = 0; v < p.nviews; ++v) {
@@ -456,6 +517,7 @@ struct HaloParams {
     int bstages;               // weight ring depth
     int BN, Co, Ksrc;
     int shift[9], kcol[9];     // per tap: patch row shift, column of the packed filter matrix
+    BnRed red;                 // optional fused reduction (see BnRed)
     long long out_sn, out_st, out_sh, out_sw, out_base;
 };
 
@@ -505,8 +567,13 @@ conv_tc_halo_kernel(const __grid_constant__ TcMaps maps, const HaloParams hp, fl
     auto b_empty = [&](int s) { return bar_base + 8u * (8 + hp.bstages + s); };
     const uint32_t tmem_ptr_addr = bar_base + 8u * (8 + 2 * hp.bstages);
     float* stat_smem = reinterpret_cast<float*>(smem_raw + (bar_base + 8u * (9 + 2 * hp.bstages) - smem_u32(smem_raw)));
-    if (stats)
+    if (stats) {
         for (int i = threadIdx.x; i < 512; i += blockDim.x) stat_smem[i] = 0.f;
+        if (hp.red.y && threadIdx.x < HALO_BN) {
+            stat_smem[512 + threadIdx.x] = hp.red.mean[threadIdx.x];
+            stat_smem[768 + threadIdx.x] = hp.red.rstd[threadIdx.x];
+        }
+    }
     const uint32_t tmem_cols = 4u * (uint32_t)hp.BN;
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.a_hi[0]) : "memory");
@@ -647,12 +714,31 @@ conv_tc_halo_kernel(const __grid_constant__ TcMaps maps, const HaloParams hp, fl
                                            __uint_as_float(v[4 * j + 1]) + __uint_as_float(u[4 * j + 1]),
                                            __uint_as_float(v[4 * j + 2]) + __uint_as_float(u[4 * j + 2]),
                                            __uint_as_float(v[4 * j + 3]) + __uint_as_float(u[4 * j + 3]));
-                    if (stats) {
-                        rs[4 * j] += o.x; rs[4 * j + 1] += o.y; rs[4 * j + 2] += o.z; rs[4 * j + 3] += o.w;
-                        rq[4 * j] += o.x * o.x; rq[4 * j + 1] += o.y * o.y; rq[4 * j + 2] += o.z * o.z; rq[4 * j + 3] += o.w * o.w;
-                    }
                     if (accumulate) { const float4 c = dst[j]; o.x += c.x; o.y += c.y; o.z += c.z; o.w += c.w; }
                     dst[j] = o;
+                    if (stats) {
+                        if (hp.red.y) {
+                            // BatchNorm-backward sums of the consumer BN (see BnRed)
+                            const size_t off = (size_t)row * hp.Co + c0 + 4 * j;
+                            const float4 yv = *reinterpret_cast<const float4*>(hp.red.y + off);
+                            uint2 mk = make_uint2(0x3f803f80u, 0x3f803f80u);
+                            if (hp.red.mask_hi) mk = *reinterpret_cast<const uint2*>(hp.red.mask_hi + off);
+                            const float* mr = stat_smem + 512 + c0 + 4 * j;
+                            const uint32_t h0 = mk.x & 0xffffu, h1 = mk.x >> 16, h2 = mk.y & 0xffffu, h3 = mk.y >> 16;
+                            const float g0 = ((h0 & 0x8000u) == 0u && (h0 & 0x7fffu) != 0u) ? o.x : 0.f;
+                            const float g1 = ((h1 & 0x8000u) == 0u && (h1 & 0x7fffu) != 0u) ? o.y : 0.f;
+                            const float g2 = ((h2 & 0x8000u) == 0u && (h2 & 0x7fffu) != 0u) ? o.z : 0.f;
+                            const float g3 = ((h3 & 0x8000u) == 0u && (h3 & 0x7fffu) != 0u) ? o.w : 0.f;
+                            rs[4 * j] += g0; rs[4 * j + 1] += g1; rs[4 * j + 2] += g2; rs[4 * j + 3] += g3;
+                            rq[4 * j] = fmaf(g0, (yv.x - mr[0]) * mr[256], rq[4 * j]);
+                            rq[4 * j + 1] = fmaf(g1, (yv.y - mr[1]) * mr[257], rq[4 * j + 1]);
+                            rq[4 * j + 2] = fmaf(g2, (yv.z - mr[2]) * mr[258], rq[4 * j + 2]);
+                            rq[4 * j + 3] = fmaf(g3, (yv.w - mr[3]) * mr[259], rq[4 * j + 3]);
+                        } else {
+                            rs[4 * j] += o.x; rs[4 * j + 1] += o.y; rs[4 * j + 2] += o.z; rs[4 * j + 3] += o.w;
+                            rq[4 * j] += o.x * o.x; rq[4 * j + 1] += o.y * o.y; rq[4 * j + 2] += o.z * o.z; rq[4 * j + 3] += o.w * o.w;
+                        }
+                    }
                 }
             }
         }
@@ -1048,7 +1134,7 @@ void set_stages(TcLaunch& L, int num_kb) {
     if (stages > num_kb) stages = num_kb;
     if (stages < 1) stages = 1;
     p.stages = stages;
-    L.smem = (size_t)stages * stage_bytes + 8 * (2 * stages + 2) + 2048 /* BN partials */ + 1024 /* alignment */;
+    L.smem = (size_t)stages * stage_bytes + 8 * (2 * stages + 2) + 4096 /* BN partials, mean, rstd */ + 1024 /* alignment */;
 }
 
 int pick_bn(int C) { return C >= 256 ? 256 : (C >= 128 ? 128 : (C >= 64 ? 64 : 32)); }
@@ -1114,7 +1200,8 @@ int make_parity_views(TcMaps& maps, const dpc_conv_geom* g, const void* x_hi, co
 // the caller (forward or flipped), `wp_*` the matching packed filter planes [64][9][64].
 // Returns 1 if it launched, 0 if the shape is not eligible, < 0 on error.
 int try_conv_halo(const void* src_hi, const void* src_lo, const void* wp_hi, const void* wp_lo, int NB, int T, int H,
-                  int W, const TapDim& tH, const TapDim& tW, float* y, int accumulate, double* stats, cudaStream_t st) {
+                  int W, const TapDim& tH, const TapDim& tW, float* y, int accumulate, double* stats, cudaStream_t st,
+                  const BnRed* red = nullptr) {
     if (const char* e = getenv("DPC_TC_HALO")) if (!atoi(e)) return 0;
     HaloParams hp;
     memset(&hp, 0, sizeof(hp));
@@ -1130,7 +1217,7 @@ int try_conv_halo(const void* src_hi, const void* src_lo, const void* wp_hi, con
     hp.patch_bytes = ((hp.bhr * hp.PW * 128 + 1023) / 1024) * 1024;
     hp.BN = 64; hp.Co = 64; hp.Ksrc = 64;
     const size_t b_stage = 2 * 64 * 128, budget = 225 * 1024;
-    const size_t fixed = 4 * (size_t)hp.patch_bytes + 1024 + 2048 + 256;
+    const size_t fixed = 4 * (size_t)hp.patch_bytes + 1024 + 4096 + 256;
     if (fixed + 2 * b_stage > budget) return 0;
     if ((int)((budget - fixed) / b_stage) < HALO_STAGES) return 0;   // the kernel is written for a 6-stage weight ring
     hp.bstages = HALO_STAGES;
@@ -1141,6 +1228,7 @@ int try_conv_halo(const void* src_hi, const void* src_lo, const void* wp_hi, con
             hp.kcol[ih * 3 + iw] = (tH.k[ih] * 3 + tW.k[iw]) * 64;
         }
     hp.out_sw = 1; hp.out_sh = W; hp.out_st = (long long)H * W; hp.out_sn = (long long)T * H * W; hp.out_base = 0;
+    if (red) hp.red = *red;
     TcMaps maps;
     const uint32_t box[5] = {64, (uint32_t)hp.PW, (uint32_t)hp.bhr, 1, 1};
     const long long sw = 64, sh = (long long)W * sw, sT = (long long)H * sh, sn = (long long)T * sT;
@@ -1151,7 +1239,7 @@ int try_conv_halo(const void* src_hi, const void* src_lo, const void* wp_hi, con
     const uint32_t bb[2] = {64, 64};
     if (make_map(&maps.b_hi, wp_hi, 2, bd, bs, bb)) return -1;
     if (make_map(&maps.b_lo, wp_lo, 2, bd, bs, bb)) return -1;
-    const size_t smem = 4 * (size_t)hp.patch_bytes + hp.bstages * b_stage + 8 * (9 + 2 * hp.bstages) + 2048 + 1024;
+    const size_t smem = 4 * (size_t)hp.patch_bytes + hp.bstages * b_stage + 8 * (9 + 2 * hp.bstages) + 4096 + 1024;
     if (cudaFuncSetAttribute(conv_tc_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
         dpc_set_error("conv_tc_halo_kernel: cannot reserve %zu bytes of shared memory", smem);
         return -1;
@@ -1227,7 +1315,7 @@ int launch_conv(TcLaunch& L, float* y, int accumulate, cudaStream_t st, double* 
         const int num_kb = p.tT.count * p.tH.count * p.tW.count * p.cchunks;
         const size_t b_tile = (size_t)p.BN * 128;
         const size_t w_bytes = (size_t)num_kb * 2 * b_tile;
-        const size_t budget = 220 * 1024;
+        const size_t budget = 218 * 1024;
         // resident weights only pay off if >= 4 activation stages still fit (measured: with 2 stages the TMA
         // latency is exposed and streaming the weights through a deeper ring is faster)
         int resident = (w_bytes + 4 * (2 * A_TILE_BYTES) + 4096 <= budget) ? 1 : 0;
@@ -1238,7 +1326,7 @@ int launch_conv(TcLaunch& L, float* y, int accumulate, cudaStream_t st, double* 
         if (stages >= 2) {
             TcParams pp = p;
             pp.stages = stages;
-            const size_t smem = (resident ? w_bytes : 0) + (size_t)stages * stage_bytes + 8 * (2 * stages + 6) + 2048 + 1024;
+            const size_t smem = (resident ? w_bytes : 0) + (size_t)stages * stage_bytes + 8 * (2 * stages + 6) + 4096 + 1024;
             DPC_CUDA(cudaFuncSetAttribute(conv_tc_persist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             const int grid = total_tiles < sms ? total_tiles : sms;
             conv_tc_persist_kernel<<<grid, 192, smem, st>>>(L.maps, pp, y, accumulate, stats, resident, total_tiles);
@@ -1403,10 +1491,15 @@ extern "C" int dpc_conv3d_fwd_tc(const dpc_conv_geom* g, const void* x_hi, const
 // dgrad, any stride in {1,2}: dx [NB,Ti,Hi,Wi,Ci] (+)= conv^T(dy planes [NB,To,Ho,Wo,Co], wd planes [Ci][taps][Co]).
 // One launch per input-parity class; with accumulate == 0 classes without taps are NOT written
 // (only possible for 1x1 strided sites, which the caller accumulates into an existing dx).
-extern "C" int dpc_conv3d_dgrad_tc(const dpc_conv_geom* g, const void* dy_hi, const void* dy_lo, const void* wd_hi,
-                                   const void* wd_lo, float* dx, int accumulate, void* stream) {
+static int dgrad_tc_impl(const dpc_conv_geom* g, const void* dy_hi, const void* dy_lo, const void* wd_hi,
+                         const void* wd_lo, float* dx, int accumulate, const BnRed* red, double* ws, void* stream) {
     if (int rc = check_geom(g, "dpc_conv3d_dgrad_tc")) return rc;
     DPC_REQUIRE(dy_hi && dy_lo && wd_hi && wd_lo && dx, "dpc_conv3d_dgrad_tc: null pointer");
+    if (red) {
+        DPC_REQUIRE(g->sT == 1 && g->sH == 1 && g->sW == 1, "dpc_conv3d_dgrad_bnred_tc: stride-1 sites only");
+        DPC_REQUIRE(red->y && red->mean && red->rstd && ws, "dpc_conv3d_dgrad_bnred_tc: null pointer");
+        DPC_CUDA(cudaMemsetAsync(ws, 0, sizeof(double) * 2 * g->Ci, as_stream(stream)));
+    }
     const int taps = g->kT * g->kH * g->kW;
     const long long rsw = 1, rsh = g->Wi, rst = (long long)g->Hi * g->Wi, rsn = (long long)g->Ti * g->Hi * g->Wi;
     for (int ct = 0; ct < g->sT; ++ct)
@@ -1429,7 +1522,7 @@ extern "C" int dpc_conv3d_dgrad_tc(const dpc_conv_geom* g, const void* dy_hi, co
                 p.cchunks = g->Co / 64; p.Ksrc = g->Co;
                 if (halo_eligible(g)) {
                     const int r = try_conv_halo(dy_hi, dy_lo, wd_hi, wd_lo, g->NB, g->Ti, g->Hi, g->Wi, p.tH, p.tW, dx,
-                                                accumulate, nullptr, as_stream(stream));
+                                                accumulate, red ? ws : nullptr, as_stream(stream), red);
                     if (r < 0) return DPC_ERR_CUDA;
                     if (r > 0) continue;
                 }
@@ -1448,9 +1541,28 @@ extern "C" int dpc_conv3d_dgrad_tc(const dpc_conv_geom* g, const void* dy_hi, co
                 if (int rc = make_map(&L.maps.b_hi, wd_hi, 2, bd, bs, bb)) return rc;
                 if (int rc = make_map(&L.maps.b_lo, wd_lo, 2, bd, bs, bb)) return rc;
                 L.grid = dim3((unsigned)(p.tiles_w * p.tiles_h * p.tiles_t * p.tiles_n), (unsigned)((g->Ci + p.BN - 1) / p.BN));
-                if (int rc = launch_conv(L, dx, accumulate, as_stream(stream))) return rc;
+                if (red) p.red = *red;
+                if (int rc = launch_conv(L, dx, accumulate, as_stream(stream), red ? ws : nullptr)) return rc;
             }
     return DPC_OK;
+}
+
+extern "C" int dpc_conv3d_dgrad_tc(const dpc_conv_geom* g, const void* dy_hi, const void* dy_lo, const void* wd_hi,
+                                   const void* wd_lo, float* dx, int accumulate, void* stream) {
+    return dgrad_tc_impl(g, dy_hi, dy_lo, wd_hi, wd_lo, dx, accumulate, nullptr, nullptr, stream);
+}
+
+// dgrad of a STRIDE-1 site with the BatchNorm-backward reduction of the consumer BN fused into the epilogue:
+// with v = the final dx (after `accumulate`), g = v * [mask_hi > 0] (mask_hi nullable: no ReLU) and
+// xhat = (y - mean) * rstd, ws [2*Ci doubles] = sum_rows g | sum_rows g * xhat   (what dpc_bn_bwd's reduce pass
+// computes from dx, `out`, `y`); mask_hi / y are [rows, Ci] like dx.
+extern "C" int dpc_conv3d_dgrad_bnred_tc(const dpc_conv_geom* g, const void* dy_hi, const void* dy_lo, const void* wd_hi,
+                                         const void* wd_lo, float* dx, int accumulate, const void* mask_hi, const float* y,
+                                         const float* mean, const float* rstd, double* ws, void* stream) {
+    BnRed red;
+    red.mask_hi = reinterpret_cast<const __nv_bfloat16*>(mask_hi);
+    red.y = y; red.mean = mean; red.rstd = rstd;
+    return dgrad_tc_impl(g, dy_hi, dy_lo, wd_hi, wd_lo, dx, accumulate, &red, ws, stream);
 }
 
 // wgrad, any stride in {1,2}: dw [Co,Ci,kT,kH,kW] = sum_positions dy (x) x; `dwp` = scratch [Co][taps][Ci] fp32

@@ -141,6 +141,11 @@ class ConvSite:
 # (the default product path); False = exact-fp32 CUDA-core kernels (reference precision, used by
 # tests to cross-check the tensor-core path).
 USE_TC = True
+# BatchNorm-backward reductions in the epilogue of the stride-1 dgrads that produce their input (dgrad_bnred).  Correct
+# (tests/test_tc_gpu.py) but OFF: measured at B = 128 the per-row gathers of mask / y in the TMEM epilogue cost more
+# than the separate coalesced reduce pass they replace (layer1 dgrad 1.06 -> 2.34 ms vs a 0.52 ms reduce; layer2
+# +0.38 vs 0.26; layer3 +0.31 vs 0.10).  Needs a smem-staged, column-contiguous epilogue to pay off.
+FUSE_BN_REDUCE = False
 
 
 @_timed('split_bf16')
@@ -193,6 +198,24 @@ class TcConvSite(ConvSite):
         lib().conv3d_dgrad_tc(self.geom, ptr(dyp[0]), ptr(dyp[1]), ptr(self.wdh), ptr(self.wdl), ptr(dx), acc, st)
         return dx
 
+    @_timed('conv_dgrad')
+    def dgrad_bnred(self, dyp, st, mask_hi, y, mean, rstd, dx=None):
+        """stride-1 dgrad + the BatchNorm-backward reduction of the BN that consumes dx (mask_hi: hi plane of that
+        BN's ReLU output or None, y / mean / rstd: its input and statistics) -> (dx, ws [2*Ci] float64)"""
+        acc = 1
+        if dx is None:
+            dx = torch.empty((self.rows_in, self.Ci), dtype=torch.float32, device=dyp[0].device)
+            acc = 0
+        ws = torch.empty(2 * self.Ci, dtype=torch.float64, device=dx.device)
+        lib().conv3d_dgrad_bnred_tc(self.geom, ptr(dyp[0]), ptr(dyp[1]), ptr(self.wdh), ptr(self.wdl), ptr(dx), acc,
+                                    ptr(mask_hi), ptr(y), ptr(mean), ptr(rstd), ptr(ws), st)
+        return dx, ws
+
+    @property
+    def stride1(self):
+        g = self.geom
+        return g.sT == 1 and g.sH == 1 and g.sW == 1
+
     @_timed('conv_wgrad')
     def wgrad(self, xp, dyp, st):
         g = self.geom
@@ -231,9 +254,12 @@ def _bn_apply(y, mean, rstd, gamma, beta, relu, rows, C, st, res=None, res_plane
 
 @_timed('bn_bwd')
 def _bn_bwd(dout, out, relu, y, mean, rstd, gamma, rows, C, st, want_g=False, out_hi=None, want_rows=True,
-            want_planes=False):
-    """-> (dy rows or None, dy planes or None, dgamma, dbeta, g or None)"""
-    ws = torch.empty(2 * C, dtype=torch.float64, device=y.device)
+            want_planes=False, ws=None):
+    """-> (dy rows or None, dy planes or None, dgamma, dbeta, g or None).  ws: the reduction [sum g | sum g*xhat]
+    when the dgrad that produced `dout` already computed it in its epilogue (TcConvSite.dgrad_bnred)"""
+    fused = ws is not None
+    if not fused:
+        ws = torch.empty(2 * C, dtype=torch.float64, device=y.device)
     dgamma = _empty((C,), y)
     dbeta = _empty((C,), y)
     dy = torch.empty_like(y) if want_rows else None
@@ -242,9 +268,10 @@ def _bn_bwd(dout, out, relu, y, mean, rstd, gamma, rows, C, st, want_g=False, ou
         planes = (torch.empty(y.shape, dtype=torch.bfloat16, device=y.device),
                   torch.empty(y.shape, dtype=torch.bfloat16, device=y.device))
     g = torch.empty_like(y) if want_g else None
-    lib().bn_bwd(ptr(dout), ptr(out), ptr(out_hi) if out is None else None, 1 if relu else 0, ptr(y), ptr(mean),
-                 ptr(rstd), ptr(gamma), ptr(ws), ptr(dgamma), ptr(dbeta), ptr(dy),
-                 ptr(planes[0]) if planes else None, ptr(planes[1]) if planes else None, ptr(g), rows, C, st)
+    fn = lib().bn_bwd_apply if fused else lib().bn_bwd
+    fn(ptr(dout), ptr(out), ptr(out_hi) if out is None else None, 1 if relu else 0, ptr(y), ptr(mean),
+       ptr(rstd), ptr(gamma), ptr(ws), ptr(dgamma), ptr(dbeta), ptr(dy),
+       ptr(planes[0]) if planes else None, ptr(planes[1]) if planes else None, ptr(g), rows, C, st)
     return dy, planes, dgamma, dbeta, g
 
 
@@ -438,7 +465,10 @@ def _backbone_backward(ctx, dout, P, side):
     st = _stream()
     main = torch.cuda.current_stream()
     G = {}
-    for rec in reversed(ctx['blocks']):
+    blocks = ctx['blocks']
+    ws_out = None          # BN-backward sums of this block's bn2, if the dgrad that produced `dout` fused them
+    for bi in reversed(range(len(blocks))):
+        rec = blocks[bi]
         b = rec['spec']
         p = b['name']
         c1, c2 = rec['c1'], rec['c2']
@@ -449,7 +479,8 @@ def _backbone_backward(ctx, dout, P, side):
         op = (lambda rows, planes: planes) if tc else (lambda rows, planes: rows)
         dy2r, dy2p, G[p + '.bn2.weight'], G[p + '.bn2.bias'], g = _bn_bwd(
             dout, rec['out'], relu, rec['y2'], rec['m2'], rec['r2'], P[p + '.bn2.weight'],
-            c2.rows_out, c2.Co, st, want_g=not has_ds, out_hi=rec['out_hi'], **kw)
+            c2.rows_out, c2.Co, st, want_g=not has_ds, out_hi=rec['out_hi'], ws=ws_out, **kw)
+        ws_out = None
         dy2 = op(dy2r, dy2p)
         if has_ds:
             cd = rec['cd']
@@ -459,11 +490,16 @@ def _backbone_backward(ctx, dout, P, side):
             dyd = op(dydr, dydp)
         del dout
         G[p + '.conv2.weight'] = _wgrad_async(c2, rec['a1_op'], dy2, main, side)
-        da1 = c2.dgrad(dy2, st)
+        # conv2 is always stride 1: its dgrad also reduces bn1's backward sums in the epilogue (FUSE_BN_REDUCE)
+        ws1 = None
+        if tc and FUSE_BN_REDUCE:
+            da1, ws1 = c2.dgrad_bnred(dy2, st, rec['a1_op'][0], rec['y1'], rec['m1'], rec['r1'])
+        else:
+            da1 = c2.dgrad(dy2, st)
         del dy2, dy2r, dy2p
         dy1r, dy1p, G[p + '.bn1.weight'], G[p + '.bn1.bias'], _ = _bn_bwd(
             da1, rec['a1'], True, rec['y1'], rec['m1'], rec['r1'], P[p + '.bn1.weight'],
-            c1.rows_out, c1.Co, st, out_hi=(rec['a1_op'][0] if tc else None), **kw)
+            c1.rows_out, c1.Co, st, out_hi=(rec['a1_op'][0] if tc else None), ws=ws1, **kw)
         dy1 = op(dy1r, dy1p)
         del da1
         G[p + '.conv1.weight'] = _wgrad_async(c1, rec['xin_op'], dy1, main, side)
@@ -472,6 +508,11 @@ def _backbone_backward(ctx, dout, P, side):
             cd.dgrad(dyd, st, dx=dx)
             G[p + '.downsample.0.weight'] = _wgrad_async(cd, rec['xin_op'], dyd, main, side)
             del dyd, dydr, dydp
+        elif tc and FUSE_BN_REDUCE and bi > 0 and c1.stride1 and blocks[bi - 1].get('out_hi') is not None:
+            # dx = g + dgrad is the previous block's output gradient: reduce that block's bn2 sums here
+            prev = blocks[bi - 1]
+            dx, ws_out = c1.dgrad_bnred(dy1, st, prev['out_hi'] if prev['spec']['final_relu'] else None,
+                                        prev['y2'], prev['m2'], prev['r2'], dx=g)
         else:
             dx = c1.dgrad(dy1, st, dx=g)          # dx = g + dgrad
         del dy1, dy1r, dy1p

@@ -75,6 +75,12 @@ int dpc_conv3d_fwd_tc(const dpc_conv_geom* g, const void* x_hi, const void* x_lo
  * input-parity class of a strided site */
 int dpc_conv3d_dgrad_tc(const dpc_conv_geom* g, const void* dy_hi, const void* dy_lo, const void* wd_hi,
                         const void* wd_lo, float* dx, int accumulate, void* stream);
+/* dgrad of a STRIDE-1 site with the BatchNorm-backward reduction of the consumer BN fused into the epilogue
+ * (resnet_2d3d.py:55-78 backward): with v = the final dx, g = v * [mask_hi > 0] (mask_hi: hi plane of that BN's
+ * ReLU output, nullable) and xhat = (y - mean) * rstd:  ws[0..Ci) = sum_rows g, ws[Ci..2Ci) = sum_rows g * xhat. */
+int dpc_conv3d_dgrad_bnred_tc(const dpc_conv_geom* g, const void* dy_hi, const void* dy_lo, const void* wd_hi,
+                              const void* wd_lo, float* dx, int accumulate, const void* mask_hi, const float* y,
+                              const float* mean, const float* rstd, double* ws, void* stream);
 /* wgrad: dw [Co,Ci,kT,kH,kW] = sum over positions dy (x) x; dwp = scratch [Co][taps][Ci] fp32 */
 int dpc_conv3d_wgrad_tc(const dpc_conv_geom* g, const void* x_hi, const void* x_lo, const void* dy_hi,
                         const void* dy_lo, float* dwp, float* dw, void* stream);
@@ -126,6 +132,12 @@ int dpc_bn_bwd(const float* dout, const float* out, const void* out_hi, int relu
                const float* mean, const float* rstd, const float* gamma, double* ws, float* dgamma,
                float* dbeta, float* dy, void* dy_hi, void* dy_lo, float* g_out, int64_t rows, int C,
                void* stream);
+/* The same with the reduction supplied by the caller (ws = [sum g | sum g*xhat], 2*C doubles): finalize + apply only.
+ * dpc_conv3d_dgrad_bnred_tc produces such a ws in the epilogue of the dgrad that computes `dout`. */
+int dpc_bn_bwd_apply(const float* dout, const float* out, const void* out_hi, int relu, const float* y,
+                     const float* mean, const float* rstd, const float* gamma, const double* ws, float* dgamma,
+                     float* dbeta, float* dy, void* dy_hi, void* dy_lo, float* g_out, int64_t rows, int C,
+                     void* stream);
 
 /* ---- stem tail: BN + ReLU + MaxPool3d((1,3,3),s(1,2,2),p(0,1,1)) in one pass ---------------
  * replaces resnet_2d3d.py:212-214,261-263.  y [NB*T,H,W,C] -> out [NB*T,H/2,W/2,C]. */

@@ -14,7 +14,12 @@ def run(NB, dims, Ci, Co, k, s, p, iters=10):
     dy = torch.randn(site.rows_out, Co, device='cuda')
     dyp = E._split(dy, st)
     res = {}
-    for name, fn in (('fwd_bn', lambda: site.fwd_bn(xp, st)), ('dgrad', lambda: site.dgrad(dyp, st)), ('wgrad', lambda: site.wgrad(xp, dyp, st))):
+    ybn = torch.randn(site.rows_in, Ci, device='cuda')
+    mask = torch.randn(site.rows_in, Ci, device='cuda').to(torch.bfloat16)
+    mean, rstd = torch.zeros(Ci, device='cuda'), torch.ones(Ci, device='cuda')
+    for name, fn in (('fwd_bn', lambda: site.fwd_bn(xp, st)), ('dgrad', lambda: site.dgrad(dyp, st)),
+                     ('dgrad_bnred', lambda: site.dgrad_bnred(dyp, st, mask, ybn, mean, rstd)),
+                     ('wgrad', lambda: site.wgrad(xp, dyp, st))):
         for _ in range(3): fn()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()

@@ -152,6 +152,28 @@ def test_conv_fwd_dgrad_wgrad_tc(case):
         L.conv3d_dgrad_tc(geom, dh.data_ptr(), dl.data_ptr(), wdh.data_ptr(), wdl.data_ptr(), dx0.data_ptr(), 0, _st())
         assert not torch.isnan(dx0).any()
         assert rel(dx0, to_rows(xr.grad)) < 5e-5
+    if s == (1, 1, 1):
+        # dgrad with the BatchNorm-backward sums of the consumer BN fused into the epilogue (engine: bn1 of a block
+        # from conv2's dgrad, the previous block's bn2 from conv1's accumulating dgrad)
+        rows_in = NB * T * H * W
+        ybn = torch.randn(rows_in, Ci, device='cuda', generator=g) * 2 + 0.3
+        out_act = torch.randn(rows_in, Ci, device='cuda', generator=g)           # the BN's ReLU output: sign = mask
+        out_hi = out_act.to(torch.bfloat16)
+        bmean = torch.randn(Ci, device='cuda', generator=g) * 0.1
+        brstd = torch.rand(Ci, device='cuda', generator=g) + 0.5
+        for acc, use_mask in ((0, True), (1, True), (1, False)):
+            dxf = base.clone() if acc else torch.full_like(base, float('nan'))
+            wsf = torch.full((2 * Ci,), float('nan'), dtype=torch.float64, device='cuda')
+            L.conv3d_dgrad_bnred_tc(geom, dh.data_ptr(), dl.data_ptr(), wdh.data_ptr(), wdl.data_ptr(), dxf.data_ptr(), acc,
+                                    out_hi.data_ptr() if use_mask else None, ybn.data_ptr(), bmean.data_ptr(),
+                                    brstd.data_ptr(), wsf.data_ptr(), _st())
+            torch.cuda.synchronize()
+            assert torch.equal(dxf, dx if acc else dx0)                            # same dx as the plain dgrad
+            gm = dxf.double() * ((out_hi.float() > 0).double() if use_mask else 1.0)
+            xhat = (ybn.double() - bmean.double()) * brstd.double()
+            ref_ws = torch.cat([gm.sum(0), (gm * xhat).sum(0)])
+            scale = float(torch.cat([gm.abs().sum(0), (gm * xhat).abs().sum(0)]).max())
+            assert float((wsf - ref_ws).abs().max()) < 2e-6 * scale, (acc, use_mask)
     # wgrad
     dwp = torch.empty(Co, taps, Ci, device='cuda')
     dw = torch.full_like(w, float('nan'))
