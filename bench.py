@@ -231,7 +231,7 @@ def run_b200(a, rank, local_rank, world):
     clocks = sampler.stop() if sampler else None
     ms_step = ms_total / a.steps
     value = world * B / (ms_step / 1e3)
-    last_loss = float(loss)
+    last_loss = float(loss.detach())
 
     # ---- end to end: pinned host input -> H2D (prefetched on a copy stream) -> step -> loss.item() ----
     e2e = None
