@@ -36,11 +36,11 @@ class EventTimer:
     def __init__(self):
         self.records = []
 
-    def start(self, tag):
+    def start(self, tag, detail=None):
         a = torch.cuda.Event(enable_timing=True)
         b = torch.cuda.Event(enable_timing=True)
         a.record()
-        return (tag, a, b)
+        return (tag, a, b, detail)
 
     def stop(self, tok):
         tok[2].record()
@@ -49,10 +49,15 @@ class EventTimer:
     def totals(self):
         torch.cuda.synchronize()
         out = {}
-        for tag, a, b in self.records:
+        for tag, a, b, _ in self.records:
             c, t = out.get(tag, (0, 0.0))
             out[tag] = (c + 1, t + a.elapsed_time(b))
         return out
+
+    def calls(self, tag):
+        """[(detail, ms)] of every call recorded under `tag`; detail = (Ci, Co, taps, rows_out, stride-1?) for conv sites"""
+        torch.cuda.synchronize()
+        return [(d, a.elapsed_time(b)) for t, a, b, d in self.records if t == tag]
 
 
 def _timed(tag):
@@ -60,7 +65,12 @@ def _timed(tag):
         def wrapped(*a, **k):
             if _TIMER is None:
                 return fn(*a, **k)
-            tok = _TIMER.start(tag)
+            site = a[0] if a and hasattr(a[0], 'geom') else None
+            detail = None
+            if site is not None:
+                g = site.geom
+                detail = (site.Ci, site.Co, site.taps, site.rows_out, g.sT * g.sH * g.sW == 1)
+            tok = _TIMER.start(tag, detail)
             try:
                 return fn(*a, **k)
             finally:
