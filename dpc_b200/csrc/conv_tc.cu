@@ -138,7 +138,16 @@ __device__ __forceinline__ void tile_epilogue_rows(const TcParams& p, float* __r
         tmem_ld_wait();
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(u[j]));
-        if (valid) {
+        const bool fast = vec && ncol0 + c0 + 32 <= p.Co && !p.red.y;      // CTA-uniform
+        if (fast) {
+            // full-sector stores through lane pairs (tc_common.cuh); v keeps this lane's own pre-accumulate row
+            float4 o[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                o[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]),
+                                   __uint_as_float(v[4 * j + 3]));
+            pair_store_rows<4>(o, y, row, valid, lane, p.Co, ncol0 + c0, accumulate != 0);
+        } else if (valid) {
             if (vec && ncol0 + c0 + 32 <= p.Co) {
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
@@ -706,40 +715,57 @@ conv_tc_halo_kernel(const __grid_constant__ TcMaps maps, const HaloParams hp, fl
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(tm_empty(buf));
-            if (valid) {
-                float4* dst = reinterpret_cast<float4*>(y + row * hp.Co + c0);
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    float4 o = make_float4(__uint_as_float(v[4 * j]) + __uint_as_float(u[4 * j]),
-                                           __uint_as_float(v[4 * j + 1]) + __uint_as_float(u[4 * j + 1]),
-                                           __uint_as_float(v[4 * j + 2]) + __uint_as_float(u[4 * j + 2]),
-                                           __uint_as_float(v[4 * j + 3]) + __uint_as_float(u[4 * j + 3]));
-                    if (accumulate) { const float4 c = dst[j]; o.x += c.x; o.y += c.y; o.z += c.z; o.w += c.w; }
-                    dst[j] = o;
-                    if (stats) {
-                        if (hp.red.y) {
-                            // BatchNorm-backward sums of the consumer BN (see BnRed)
-                            const size_t off = (size_t)row * hp.Co + c0 + 4 * j;
-                            const float4 yv = *reinterpret_cast<const float4*>(hp.red.y + off);
-                            uint2 mk = make_uint2(0x3f803f80u, 0x3f803f80u);
-                            if (hp.red.mask_hi) mk = *reinterpret_cast<const uint2*>(hp.red.mask_hi + off);
-                            const float* mr = stat_smem + 512 + c0 + 4 * j;
-                            const uint32_t h0 = mk.x & 0xffffu, h1 = mk.x >> 16, h2 = mk.y & 0xffffu, h3 = mk.y >> 16;
-                            const float g0 = ((h0 & 0x8000u) == 0u && (h0 & 0x7fffu) != 0u) ? o.x : 0.f;
-                            const float g1 = ((h1 & 0x8000u) == 0u && (h1 & 0x7fffu) != 0u) ? o.y : 0.f;
-                            const float g2 = ((h2 & 0x8000u) == 0u && (h2 & 0x7fffu) != 0u) ? o.z : 0.f;
-                            const float g3 = ((h3 & 0x8000u) == 0u && (h3 & 0x7fffu) != 0u) ? o.w : 0.f;
-                            rs[4 * j] += g0; rs[4 * j + 1] += g1; rs[4 * j + 2] += g2; rs[4 * j + 3] += g3;
-                            rq[4 * j] = fmaf(g0, (yv.x - mr[0]) * mr[256], rq[4 * j]);
-                            rq[4 * j + 1] = fmaf(g1, (yv.y - mr[1]) * mr[257], rq[4 * j + 1]);
-                            rq[4 * j + 2] = fmaf(g2, (yv.z - mr[2]) * mr[258], rq[4 * j + 2]);
-                            rq[4 * j + 3] = fmaf(g3, (yv.w - mr[3]) * mr[259], rq[4 * j + 3]);
-                        } else {
-                            rs[4 * j] += o.x; rs[4 * j + 1] += o.y; rs[4 * j + 2] += o.z; rs[4 * j + 3] += o.w;
-                            rq[4 * j] += o.x * o.x; rq[4 * j + 1] += o.y * o.y; rq[4 * j + 2] += o.z * o.z; rq[4 * j + 3] += o.w * o.w;
+            if (hp.red.y) {
+                if (valid) {
+                    float4* dst = reinterpret_cast<float4*>(y + row * hp.Co + c0);
+    #pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        float4 o = make_float4(__uint_as_float(v[4 * j]) + __uint_as_float(u[4 * j]),
+                                               __uint_as_float(v[4 * j + 1]) + __uint_as_float(u[4 * j + 1]),
+                                               __uint_as_float(v[4 * j + 2]) + __uint_as_float(u[4 * j + 2]),
+                                               __uint_as_float(v[4 * j + 3]) + __uint_as_float(u[4 * j + 3]));
+                        if (accumulate) { const float4 c = dst[j]; o.x += c.x; o.y += c.y; o.z += c.z; o.w += c.w; }
+                        dst[j] = o;
+                        if (stats) {
+                            if (hp.red.y) {
+                                // BatchNorm-backward sums of the consumer BN (see BnRed)
+                                const size_t off = (size_t)row * hp.Co + c0 + 4 * j;
+                                const float4 yv = *reinterpret_cast<const float4*>(hp.red.y + off);
+                                uint2 mk = make_uint2(0x3f803f80u, 0x3f803f80u);
+                                if (hp.red.mask_hi) mk = *reinterpret_cast<const uint2*>(hp.red.mask_hi + off);
+                                const float* mr = stat_smem + 512 + c0 + 4 * j;
+                                const uint32_t h0 = mk.x & 0xffffu, h1 = mk.x >> 16, h2 = mk.y & 0xffffu, h3 = mk.y >> 16;
+                                const float g0 = ((h0 & 0x8000u) == 0u && (h0 & 0x7fffu) != 0u) ? o.x : 0.f;
+                                const float g1 = ((h1 & 0x8000u) == 0u && (h1 & 0x7fffu) != 0u) ? o.y : 0.f;
+                                const float g2 = ((h2 & 0x8000u) == 0u && (h2 & 0x7fffu) != 0u) ? o.z : 0.f;
+                                const float g3 = ((h3 & 0x8000u) == 0u && (h3 & 0x7fffu) != 0u) ? o.w : 0.f;
+                                rs[4 * j] += g0; rs[4 * j + 1] += g1; rs[4 * j + 2] += g2; rs[4 * j + 3] += g3;
+                                rq[4 * j] = fmaf(g0, (yv.x - mr[0]) * mr[256], rq[4 * j]);
+                                rq[4 * j + 1] = fmaf(g1, (yv.y - mr[1]) * mr[257], rq[4 * j + 1]);
+                                rq[4 * j + 2] = fmaf(g2, (yv.z - mr[2]) * mr[258], rq[4 * j + 2]);
+                                rq[4 * j + 3] = fmaf(g3, (yv.w - mr[3]) * mr[259], rq[4 * j + 3]);
+                            } else {
+                                rs[4 * j] += o.x; rs[4 * j + 1] += o.y; rs[4 * j + 2] += o.z; rs[4 * j + 3] += o.w;
+                                rq[4 * j] += o.x * o.x; rq[4 * j + 1] += o.y * o.y; rq[4 * j + 2] += o.z * o.z; rq[4 * j + 3] += o.w * o.w;
+                            }
                         }
                     }
                 }
+            } else {
+                float4 o[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    o[j] = make_float4(__uint_as_float(v[4 * j]) + __uint_as_float(u[4 * j]),
+                                       __uint_as_float(v[4 * j + 1]) + __uint_as_float(u[4 * j + 1]),
+                                       __uint_as_float(v[4 * j + 2]) + __uint_as_float(u[4 * j + 2]),
+                                       __uint_as_float(v[4 * j + 3]) + __uint_as_float(u[4 * j + 3]));
+                    if (stats && valid) {          // BatchNorm statistics of the conv output (forward: no accumulate)
+                        rs[4 * j] += o[j].x; rs[4 * j + 1] += o[j].y; rs[4 * j + 2] += o[j].z; rs[4 * j + 3] += o[j].w;
+                        rq[4 * j] += o[j].x * o[j].x; rq[4 * j + 1] += o[j].y * o[j].y;
+                        rq[4 * j + 2] += o[j].z * o[j].z; rq[4 * j + 3] += o[j].w * o[j].w;
+                    }
+                }
+                pair_store_rows<4>(o, y, row, valid, lane, hp.Co, c0, accumulate != 0);      // full-sector stores
             }
         }
         if (stats) {

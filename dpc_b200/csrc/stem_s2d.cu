@@ -19,6 +19,9 @@
 namespace {
 
 constexpr int S2D_CH = 16, S2D_TAPS = 16, S2D_BN = 64;
+constexpr int S2D_EC = 16;                                  // output columns per epilogue warp
+constexpr int S2D_NPB_MAX = 4;                              // patch buffers (and per-tile completion barriers) in flight
+constexpr int S2D_FWD_THREADS = 64 + 32 * 4 * (S2D_BN / S2D_EC);   // producer + MMA warp + epilogue warps
 constexpr uint32_t S2D_W_BYTES = S2D_TAPS * 2 * S2D_BN * 32;      // 64 KB: per tap [W_hi (64 rows) ; W_lo (64 rows)] x 32 B
 
 struct S2dMaps { CUtensorMap x_hi, x_lo, w; };
@@ -28,6 +31,7 @@ struct S2dParams {
     int Ho, Wo, T;
     int tiles_per_frame, total_tiles;
     int patch_bytes;           // one plane of the patch, rounded up to 1024
+    int npb;                   // patch buffers in flight (2 .. S2D_NPB_MAX, as shared memory allows)
     int shift[S2D_TAPS];       // patch row shift per tap
 };
 
@@ -88,7 +92,7 @@ __global__ void stem_s2d_wpack_kernel(const float* __restrict__ w, __nv_bfloat16
 // version 1 (bit 46) | layout type 6 (SWIZZLE_32B, bits 61-63); low word = start address >> 4 | LBO field (unused).
 constexpr uint64_t S2D_DHI = 0xC0004010ull << 32;
 
-__global__ void __launch_bounds__(320, 1)
+__global__ void __launch_bounds__(S2D_FWD_THREADS, 1)
 stem_s2d_fwd_kernel(const __grid_constant__ S2dMaps maps, const S2dParams hp, float* __restrict__ y, double* __restrict__ stats) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -96,19 +100,23 @@ stem_s2d_fwd_kernel(const __grid_constant__ S2dMaps maps, const S2dParams hp, fl
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t pbase = base + S2D_W_BYTES;
     const uint32_t pbuf = 2u * (uint32_t)hp.patch_bytes;
-    const uint32_t bar_base = pbase + 2u * pbuf;
+    const int NPB = hp.npb;
+    const uint32_t bar_base = pbase + (uint32_t)NPB * pbuf;
+    // p_full[b]: patch b landed;  tm_full[b] (b = tile % NPB): the tile's MMAs retired -- read by the epilogue
+    // (accumulator ready) AND by the producer (patch buffer b free again);  tm_empty[a] (a = tile & 1): TMEM buffer drained
     auto p_full = [&](int b) { return bar_base + 8u * b; };
-    auto tm_full = [&](int b) { return bar_base + 8u * (2 + b); };
-    auto tm_empty = [&](int b) { return bar_base + 8u * (4 + b); };
-    const uint32_t w_full = bar_base + 48u, tmem_ptr_addr = bar_base + 56u;
-    float* stat_smem = reinterpret_cast<float*>(smem_raw + (bar_base + 64u - smem_u32(smem_raw)));
+    auto tm_full = [&](int b) { return bar_base + 8u * (S2D_NPB_MAX + b); };
+    auto tm_empty = [&](int b) { return bar_base + 8u * (2 * S2D_NPB_MAX + b); };
+    const uint32_t w_full = bar_base + 8u * (2 * S2D_NPB_MAX + 2), tmem_ptr_addr = w_full + 8u;
+    float* stat_smem = reinterpret_cast<float*>(smem_raw + (w_full + 16u - smem_u32(smem_raw)));
     if (stats && threadIdx.x < 128) stat_smem[threadIdx.x] = 0.f;
     const uint32_t tmem_cols = 4u * S2D_BN;
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.x_hi) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.x_lo) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.w) : "memory");
-        for (int b = 0; b < 2; ++b) { mbar_init(p_full(b), 1); mbar_init(tm_full(b), 1); mbar_init(tm_empty(b), 8); }
+        for (int b = 0; b < NPB; ++b) { mbar_init(p_full(b), 1); mbar_init(tm_full(b), 1); }
+        for (int b = 0; b < 2; ++b) mbar_init(tm_empty(b), 4 * (S2D_BN / S2D_EC));
         mbar_init(w_full, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -134,8 +142,8 @@ stem_s2d_fwd_kernel(const __grid_constant__ S2dMaps maps, const S2dParams hp, fl
             for (int j = 0; j < 8; ++j) tma_load_2d(&maps.w, base + j * 8192, w_full, 0, j * 256);
             const uint32_t patch_tx = 2u * (uint32_t)(hp.bhr * hp.PW) * 32u;
             for (int i = 0; i < my_tiles; ++i) {
-                const int b = i & 1;
-                if (i >= 2) mbar_wait(tm_full(b), ((uint32_t)(i - 2) >> 1) & 1u);      // tile i-2 has retired: buffer free
+                const int b = i % NPB;
+                if (i >= NPB) mbar_wait(tm_full(b), ((uint32_t)(i / NPB) - 1u) & 1u);   // tile i-NPB has retired: buffer free
                 int n, t, f0, hrow0;
                 tile_origin(i, n, t, f0, hrow0);
                 mbar_expect_tx(p_full(b), patch_tx);
@@ -160,9 +168,10 @@ stem_s2d_fwd_kernel(const __grid_constant__ S2dMaps maps, const S2dParams hp, fl
                 const uint32_t td = tmem_base + (uint32_t)(buf * 2 * S2D_BN), tcx = td + (uint32_t)S2D_BN;
                 int n, t, f0, hrow0;
                 tile_origin(i, n, t, f0, hrow0);
-                const uint32_t a_lo32 = ((pbase + buf * pbuf + (uint32_t)(f0 - hrow0 * hp.PW) * 32u) >> 4) | 0x10000u;
+                const int pb = i % NPB;
+                const uint32_t a_lo32 = ((pbase + pb * pbuf + (uint32_t)(f0 - hrow0 * hp.PW) * 32u) >> 4) | 0x10000u;
                 mbar_wait(tm_empty(buf), (((uint32_t)i >> 1) & 1u) ^ 1u);
-                mbar_wait(p_full(buf), ((uint32_t)i >> 1) & 1u);
+                mbar_wait(p_full(pb), (uint32_t)(i / NPB) & 1u);
                 tc_fence_after();
 #pragma unroll
                 for (int tap = 0; tap < S2D_TAPS; ++tap) {
@@ -170,16 +179,18 @@ stem_s2d_fwd_kernel(const __grid_constant__ S2dMaps maps, const S2dParams hp, fl
                     umma_bf16(td, S2D_DHI | (uint64_t)ahi, S2D_DHI | (uint64_t)b, idesc2, tap ? 1u : 0u);
                     umma_bf16(tcx, S2D_DHI | (uint64_t)alo, S2D_DHI | (uint64_t)b, idesc1, 1u);
                 }
-                umma_commit(tm_full(buf));
+                umma_commit(tm_full(pb));
             }
         }
     } else {
-        // epilogue: 8 warps = 4 TMEM lane quarters (warp % 4) x two 32-column halves; BatchNorm partial sums stay in
-        // registers (one row per lane) across all tiles of the CTA and are transposed once at the end
-        const int q = warp & 3, c0 = ((warp - 2) >> 2) * 32;
-        float rs[32], rq[32];
+        // epilogue: 16 warps = 4 TMEM lane quarters (warp % 4) x four 16-column groups (the epilogue, not the MMAs,
+        // bounds this kernel: ncu showed the 8-warp version stalled on the TMEM loads with the tensor pipe 43 % active);
+        // BatchNorm partial sums stay in registers (one row per lane) across all tiles of the CTA and are transposed
+        // once at the end
+        const int q = warp & 3, c0 = ((warp - 2) >> 2) * S2D_EC;
+        float rs[S2D_EC], rq[S2D_EC];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) { rs[j] = 0.f; rq[j] = 0.f; }
+        for (int j = 0; j < S2D_EC; ++j) { rs[j] = 0.f; rq[j] = 0.f; }
         for (int i = 0; i < my_tiles; ++i) {
             const int buf = i & 1;
             const uint32_t td = tmem_base + (uint32_t)(buf * 2 * S2D_BN), tcx = td + (uint32_t)S2D_BN;
@@ -189,46 +200,53 @@ stem_s2d_fwd_kernel(const __grid_constant__ S2dMaps maps, const S2dParams hp, fl
             const int h = f / hp.PW, w = f - h * hp.PW;
             const bool valid = h < hp.Ho && w < hp.Wo;
             const long long row = (((long long)n * hp.T + t) * hp.Ho + h) * hp.Wo + w;
-            mbar_wait(tm_full(buf), ((uint32_t)i >> 1) & 1u);
+            mbar_wait(tm_full(i % NPB), (uint32_t)(i / NPB) & 1u);
             tc_fence_after();
-            uint32_t v[32], u[32];
-            tmem_ld32_nowait(td + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
-            tmem_ld32_nowait(tcx + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, u);
+            uint32_t v[S2D_EC], u[S2D_EC];
+            tmem_ld16_nowait(td + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+            tmem_ld16_nowait(tcx + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, u);
             tmem_ld_wait();
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(tm_empty(buf));
-            if (valid) {
-                float4* dst = reinterpret_cast<float4*>(y + row * S2D_BN + c0);
+            float4 o[S2D_EC / 4];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const float4 o = make_float4(__uint_as_float(v[4 * j]) + __uint_as_float(u[4 * j]),
-                                                 __uint_as_float(v[4 * j + 1]) + __uint_as_float(u[4 * j + 1]),
-                                                 __uint_as_float(v[4 * j + 2]) + __uint_as_float(u[4 * j + 2]),
-                                                 __uint_as_float(v[4 * j + 3]) + __uint_as_float(u[4 * j + 3]));
-                    if (stats) {
-                        rs[4 * j] += o.x; rs[4 * j + 1] += o.y; rs[4 * j + 2] += o.z; rs[4 * j + 3] += o.w;
-                        rq[4 * j] += o.x * o.x; rq[4 * j + 1] += o.y * o.y; rq[4 * j + 2] += o.z * o.z; rq[4 * j + 3] += o.w * o.w;
-                    }
-                    dst[j] = o;
+            for (int j = 0; j < S2D_EC / 4; ++j) {
+                o[j] = make_float4(__uint_as_float(v[4 * j]) + __uint_as_float(u[4 * j]),
+                                   __uint_as_float(v[4 * j + 1]) + __uint_as_float(u[4 * j + 1]),
+                                   __uint_as_float(v[4 * j + 2]) + __uint_as_float(u[4 * j + 2]),
+                                   __uint_as_float(v[4 * j + 3]) + __uint_as_float(u[4 * j + 3]));
+                if (stats && valid) {
+                    rs[4 * j] += o[j].x; rs[4 * j + 1] += o[j].y; rs[4 * j + 2] += o[j].z; rs[4 * j + 3] += o[j].w;
+                    rq[4 * j] += o[j].x * o[j].x; rq[4 * j + 1] += o[j].y * o[j].y;
+                    rq[4 * j + 2] += o[j].z * o[j].z; rq[4 * j + 3] += o[j].w * o[j].w;
                 }
             }
+            // Stores: a lane pair (rows 2k, 2k+1) swaps halves of each 8-column group, so that one STG.128 of the pair
+            // fills a whole 32-byte sector of ONE row instead of two half sectors of two rows (ncu: the row-per-lane
+            // stores issued 2x the L2 write sectors and the L2 was 72 % busy).
+            pair_store_rows<S2D_EC / 8>(o, y, row, valid, lane, S2D_BN, c0, false);
         }
         if (stats) {
-            // lane l ends up with column c0 + l summed over the warp's 32 rows (31-shuffle transposing butterfly)
+            // transposing butterfly over the warp's 32 rows: after the halving steps lane l holds column c0 + (l >> 1)
+            // summed over 16 rows; the last exchange adds the other 16
 #pragma unroll
-            for (int off = 16; off >= 1; off >>= 1) {
+            for (int off = 16, nn = S2D_EC / 2; nn >= 1; off >>= 1, nn >>= 1) {
                 const bool up = (lane & off) != 0;
 #pragma unroll
-                for (int i = 0; i < off; ++i) {
-                    const float s_send = up ? rs[i] : rs[i + off], s_keep = up ? rs[i + off] : rs[i];
-                    const float q_send = up ? rq[i] : rq[i + off], q_keep = up ? rq[i + off] : rq[i];
+                for (int i = 0; i < nn; ++i) {
+                    const float s_send = up ? rs[i] : rs[i + nn], s_keep = up ? rs[i + nn] : rs[i];
+                    const float q_send = up ? rq[i] : rq[i + nn], q_keep = up ? rq[i + nn] : rq[i];
                     rs[i] = s_keep + __shfl_xor_sync(0xffffffffu, s_send, off);
                     rq[i] = q_keep + __shfl_xor_sync(0xffffffffu, q_send, off);
                 }
             }
-            atomicAdd(&stat_smem[c0 + lane], rs[0]);
-            atomicAdd(&stat_smem[64 + c0 + lane], rq[0]);
+            rs[0] += __shfl_xor_sync(0xffffffffu, rs[0], 1);
+            rq[0] += __shfl_xor_sync(0xffffffffu, rq[0], 1);
+            if ((lane & 1) == 0) {
+                atomicAdd(&stat_smem[c0 + (lane >> 1)], rs[0]);
+                atomicAdd(&stat_smem[64 + c0 + (lane >> 1)], rq[0]);
+            }
         }
     }
     tc_fence_before();
@@ -425,7 +443,9 @@ extern "C" int dpc_stem_conv_fwd_s2d(const void* x2_hi, const void* x2_lo, const
     hp.patch_bytes = ((hp.bhr * hp.PW * 32 + 1023) / 1024) * 1024;
     for (int a = 0; a < 4; ++a)
         for (int b = 0; b < 4; ++b) hp.shift[a * 4 + b] = a * hp.PW + b;
-    const size_t smem = S2D_W_BYTES + 4 * (size_t)hp.patch_bytes + 64 + 512 + 1024;
+    hp.npb = S2D_NPB_MAX;
+    while (hp.npb > 2 && S2D_W_BYTES + 2 * hp.npb * (size_t)hp.patch_bytes + 128 + 512 + 1024 > 227 * 1024) --hp.npb;
+    const size_t smem = S2D_W_BYTES + 2 * hp.npb * (size_t)hp.patch_bytes + 128 + 512 + 1024;
     DPC_REQUIRE(smem <= 227 * 1024, "dpc_stem_conv_fwd_s2d: patch does not fit shared memory (W = %d)", W);
     auto enc = s2d_encode();
     DPC_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled entry point not available");
@@ -453,7 +473,7 @@ extern "C" int dpc_stem_conv_fwd_s2d(const void* x2_hi, const void* x2_lo, const
     DPC_CUDA(cudaFuncSetAttribute(stem_s2d_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int sms = dpc_num_sms();
     const int grid = hp.total_tiles < sms ? hp.total_tiles : sms;
-    stem_s2d_fwd_kernel<<<grid, 320, smem, st>>>(maps, hp, y, bn_ws);
+    stem_s2d_fwd_kernel<<<grid, S2D_FWD_THREADS, smem, st>>>(maps, hp, y, bn_ws);
     DPC_LAUNCH_CHECK();
     return DPC_OK;
 }

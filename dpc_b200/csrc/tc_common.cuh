@@ -79,6 +79,14 @@ __device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t (&v)[3
           "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
         : "r"(taddr));
 }
+__device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t (&v)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr));
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
     tmem_ld32_nowait(taddr, v);
@@ -93,6 +101,45 @@ __device__ __forceinline__ bool elect_one() {
         "selp.u32 %0, 1, 0, P;\n\t"
         "}" : "=r"(pred));
     return pred != 0;
+}
+
+// Row-per-lane epilogue stores with full sectors.  After tcgen05.ld every lane holds ONE output row; a plain STG.128
+// per lane touches 32 different rows, i.e. 32 half-filled 32-byte sectors per instruction (measured on the stem
+// forward: 2x the L2 write sectors, L2 72 % busy).  Here `o` holds NG groups of 8 consecutive columns (two float4)
+// of this lane's row; lanes 2k / 2k+1 exchange one float4 per group and store
+// [row 2k | row 2k+1] x [cols 0-3 | cols 4-7], so each instruction of the pair fills whole sectors of one row.
+// `o` must be computed by ALL lanes (shuffles); `accumulate` adds the existing values first.
+template <int NG>
+__device__ __forceinline__ void pair_store_rows(const float4 (&o)[2 * NG], float* __restrict__ y, long long row, bool valid,
+                                                int lane, int ld, int c0, bool accumulate) {
+    const long long row_p = __shfl_xor_sync(0xffffffffu, row, 1);
+    const bool valid_p = __shfl_xor_sync(0xffffffffu, (int)valid, 1) != 0;
+    const bool odd = (lane & 1) != 0;
+    const long long row_e = odd ? row_p : row, row_o = odd ? row : row_p;
+    const bool val_e = odd ? valid_p : valid, val_o = odd ? valid : valid_p;
+    float* pe = y + (val_e ? row_e : 0) * ld + c0 + (odd ? 4 : 0);
+    float* po = y + (val_o ? row_o : 0) * ld + c0 + (odd ? 4 : 0);
+#pragma unroll
+    for (int g = 0; g < NG; ++g) {
+        const float4 a = o[2 * g], b = o[2 * g + 1];
+        const float4 send = odd ? a : b;
+        float4 recv;
+        recv.x = __shfl_xor_sync(0xffffffffu, send.x, 1);
+        recv.y = __shfl_xor_sync(0xffffffffu, send.y, 1);
+        recv.z = __shfl_xor_sync(0xffffffffu, send.z, 1);
+        recv.w = __shfl_xor_sync(0xffffffffu, send.w, 1);
+        float4 s1 = odd ? recv : a, s2 = odd ? b : recv;
+        if (val_e) {
+            float4* d = reinterpret_cast<float4*>(pe + 8 * g);
+            if (accumulate) { const float4 c = *d; s1.x += c.x; s1.y += c.y; s1.z += c.z; s1.w += c.w; }
+            *d = s1;
+        }
+        if (val_o) {
+            float4* d = reinterpret_cast<float4*>(po + 8 * g);
+            if (accumulate) { const float4 c = *d; s2.x += c.x; s2.y += c.y; s2.z += c.z; s2.w += c.w; }
+            *d = s2;
+        }
+    }
 }
 
 // K-major, 128B-swizzled operand tile: rows at 128-byte pitch, 8-row atoms 1024 bytes apart.
