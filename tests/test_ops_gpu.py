@@ -81,7 +81,7 @@ def test_conv3d_fwd_dgrad_wgrad(case):
     assert rel(dw, wref.grad) < 5e-5
 
 
-@pytest.mark.parametrize('NB,T,H,W', [(2, 5, 64, 64), (3, 2, 32, 48), (1, 1, 28, 20)])
+@pytest.mark.parametrize('NB,T,H,W', [(2, 5, 64, 64), (3, 2, 32, 48), (1, 1, 28, 20), (1, 2, 27, 21)])
 def test_stem_conv(NB, T, H, W):
     L = _lib()
     g = torch.Generator(device='cuda').manual_seed(2)
