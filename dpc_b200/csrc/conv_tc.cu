@@ -11,8 +11,12 @@
 //   through per-parity views of the tensor (base pointer offset + doubled strides in the tensor map);
 // * shared-memory tiles are 128B-swizzled; forward/dgrad use K-major UMMA descriptors (K = channels),
 //   wgrad uses MN-major descriptors over the SAME boxes (K = positions);
-// * warp 0 = TMA producer, warp 1 = MMA issuer (one elected lane) + TMEM owner, warps 2-5 = epilogue
-//   (tcgen05.ld -> registers -> global), with an mbarrier full/empty ring between them.
+// * warp 0 = TMA producer, warp 1 = MMA issuer (one elected lane) + TMEM owner, warps 2-5 (2-9 in the halo kernel)
+//   = epilogue (tcgen05.ld -> registers -> lane-pair exchange -> full-sector stores), with an mbarrier full/empty
+//   ring between them;
+// * three schedules: conv_tc_kernel (one tile per CTA, 2 CTAs/SM, any shape), conv_tc_persist_kernel (Co <= 128:
+//   persistent, double-buffered TMEM) and the halo-patch kernels conv_tc_halo_kernel / wgrad_halo_kernel for the
+//   stride-1 1x3x3 64 -> 64 sites (one TMA box per tile, taps = row-shifted descriptors); see DESIGN.md section 5.
 //
 // Replaces nn.Conv3d fwd/bwd at backbone/resnet_2d3d.py:13-31,241-244 and torch.matmul at
 // dpc/model_3d.py:83.

@@ -7,9 +7,11 @@ Two stages, each a forward/backward pair driven from a torch.autograd.Function
   head     : avg-pool/ReLU split, ConvGRU, predictor loop, score matmul
              (/root/reference/dpc/model_3d.py:53-83, backbone/convrnn.py:24-34,62-88)
 
-Data layout in HBM: activations are channels-last rows [NB*T*H*W, C] fp32; the caller's NCDHW
-video block is read directly by the stem kernel.  PyTorch provides memory (caching allocator) and
-the current stream only; every FLOP below is issued through libdpc_b200.so.
+Data layout in HBM: activations are channels-last rows [NB*T*H*W, C] fp32 (+ split-bf16 hi/lo planes
+for tensor-core operands); the caller's NCDHW video block is repacked once per step into 2x2
+space-to-depth split-bf16 planes that the stem forward and wgrad read through TMA.  PyTorch provides
+memory (caching allocator) and the current stream only; every FLOP below is issued through
+libdpc_b200.so.
 """
 import math
 
