@@ -6,6 +6,7 @@
 // Replaces nn.BatchNorm3d + relu_ + `out += residual` (backbone/resnet_2d3d.py:55-78,91-114,
 // 212-214,243) and F.avg_pool3d + relu (dpc/model_3d.py:53-57).
 #include "common.cuh"
+#include <cuda_bf16.h>
 
 namespace {
 
@@ -97,16 +98,17 @@ __device__ __forceinline__ uint32_t f2bf_rn(float f) {      // round-to-nearest-
     uint32_t u = __float_as_uint(f);
     return (u + 0x7FFFu + ((u >> 16) & 1u)) >> 16;
 }
+// hi = bf16(v), lo = bf16(v - hi), packed pairwise with the hardware cvt.rn.bf16x2.f32 (round-to-nearest-even, the
+// same rounding as dpc_split_bf16); ~14 instructions per float4 instead of ~50 with integer bit arithmetic
 __device__ __forceinline__ void st4_planes(void* hi, void* lo, long long off, float4 v) {
-    float f[4] = {v.x, v.y, v.z, v.w};
-    uint32_t h[4], l[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        h[j] = f2bf_rn(f[j]);
-        l[j] = f2bf_rn(f[j] - bf16_bits_to_float(h[j]));
-    }
-    *reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(hi) + off) = make_uint2(h[0] | (h[1] << 16), h[2] | (h[3] << 16));
-    *reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(lo) + off) = make_uint2(l[0] | (l[1] << 16), l[2] | (l[3] << 16));
+    const __nv_bfloat162 h01 = __floats2bfloat162_rn(v.x, v.y), h23 = __floats2bfloat162_rn(v.z, v.w);
+    const float2 f01 = __bfloat1622float2(h01), f23 = __bfloat1622float2(h23);
+    const __nv_bfloat162 l01 = __floats2bfloat162_rn(v.x - f01.x, v.y - f01.y);
+    const __nv_bfloat162 l23 = __floats2bfloat162_rn(v.z - f23.x, v.w - f23.y);
+    *reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(hi) + off) =
+        make_uint2(*reinterpret_cast<const uint32_t*>(&h01), *reinterpret_cast<const uint32_t*>(&h23));
+    *reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(lo) + off) =
+        make_uint2(*reinterpret_cast<const uint32_t*>(&l01), *reinterpret_cast<const uint32_t*>(&l23));
 }
 
 // RES: 0 none, 1 raw residual (fp32 rows or bf16 planes), 2 batch-normalised residual (downsample branch)
