@@ -227,6 +227,8 @@ __global__ void __launch_bounds__(THREADS) bn_bwd_apply_kernel(const float* __re
 }
 
 // ---- stem tail: BN + ReLU + MaxPool (1,3,3)/(1,2,2)/(0,1,1) ------------------------------------
+// Each thread produces TWO horizontally adjacent pooled outputs (wo0 = 2*wq, wo0 + 1): their windows share one of
+// three input columns, so 15 loads / affine transforms serve two outputs instead of 18.
 __global__ void __launch_bounds__(THREADS) bn_relu_maxpool_fwd_kernel(const float* __restrict__ y,
                                                                        const float* mean, const float* rstd,
                                                                        const float* gamma, const float* beta,
@@ -235,26 +237,29 @@ __global__ void __launch_bounds__(THREADS) bn_relu_maxpool_fwd_kernel(const floa
     const int C4 = C / 4, rg = THREADS / C4;
     const int cq = threadIdx.x % C4, rl = threadIdx.x / C4;
     const Affine4 a = make_affine(mean, rstd, gamma, beta, cq * 4);
-    const long long rows = (long long)NT * Ho * Wo;
+    const int Wo2 = (Wo + 1) / 2;
+    const long long rows = (long long)NT * Ho * Wo2;
     for (long long r = (long long)blockIdx.x * rg + rl; r < rows; r += (long long)gridDim.x * rg) {
-        int wo = (int)(r % Wo);
-        int ho = (int)((r / Wo) % Ho);
-        long long nt = r / ((long long)Wo * Ho);
-        float4 best = make_float4(0.f, 0.f, 0.f, 0.f);   // ReLU output is >= 0, so 0 is the identity
+        const int wq = (int)(r % Wo2);
+        const int ho = (int)((r / Wo2) % Ho);
+        const long long nt = r / ((long long)Wo2 * Ho);
+        float4 b0 = make_float4(0.f, 0.f, 0.f, 0.f), b1 = b0;   // ReLU output is >= 0, so 0 is the identity
 #pragma unroll
         for (int dh = -1; dh <= 1; ++dh) {
-            int h = 2 * ho + dh;
+            const int h = 2 * ho + dh;
             if (h < 0 || h >= H) continue;
 #pragma unroll
-            for (int dw = -1; dw <= 1; ++dw) {
-                int w = 2 * wo + dw;
+            for (int c = 0; c < 5; ++c) {
+                const int w = 4 * wq - 1 + c;
                 if (w < 0 || w >= W) continue;
-                float4 v = affine(ld4(y + ((nt * H + h) * W + w) * C + cq * 4), a);
-                best.x = fmaxf(best.x, v.x); best.y = fmaxf(best.y, v.y);
-                best.z = fmaxf(best.z, v.z); best.w = fmaxf(best.w, v.w);
+                const float4 v = affine(ld4(y + ((nt * H + h) * W + w) * C + cq * 4), a);
+                if (c <= 2) { b0.x = fmaxf(b0.x, v.x); b0.y = fmaxf(b0.y, v.y); b0.z = fmaxf(b0.z, v.z); b0.w = fmaxf(b0.w, v.w); }
+                if (c >= 2) { b1.x = fmaxf(b1.x, v.x); b1.y = fmaxf(b1.y, v.y); b1.z = fmaxf(b1.z, v.z); b1.w = fmaxf(b1.w, v.w); }
             }
         }
-        st4(out + r * C + cq * 4, best);
+        float* o = out + ((nt * Ho + ho) * Wo + 2 * wq) * C + cq * 4;
+        st4(o, b0);
+        if (2 * wq + 1 < Wo) st4(o + C, b1);
     }
 }
 
@@ -627,7 +632,7 @@ extern "C" int dpc_bn_relu_maxpool_fwd(const float* y, const float* mean, const 
     if (int rc = check_c(C, "dpc_bn_relu_maxpool_fwd")) return rc;
     const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
     const int rg = THREADS / (C / 4);
-    bn_relu_maxpool_fwd_kernel<<<stream_grid((long long)NT * Ho * Wo, rg), THREADS, 0, as_stream(stream)>>>(
+    bn_relu_maxpool_fwd_kernel<<<stream_grid((long long)NT * Ho * ((Wo + 1) / 2), rg), THREADS, 0, as_stream(stream)>>>(
         y, mean, rstd, gamma, beta, out, NT, H, W, Ho, Wo, C);
     DPC_LAUNCH_CHECK();
     return DPC_OK;
