@@ -10,6 +10,7 @@ A functional, state-dict driven restatement (fp32, or fp64 on request) of the re
     DPC_RNN.forward                      /root/reference/dpc/model_3d.py:46-98
     ResNet2d3d_full.forward              /root/reference/backbone/resnet_2d3d.py:259-270
     BasicBlock2d / BasicBlock3d.forward  /root/reference/backbone/resnet_2d3d.py:100-116, 64-80
+    Bottleneck2d / Bottleneck3d.forward  /root/reference/backbone/resnet_2d3d.py:181-200, 139-158  (oracle only so far)
     ConvGRUCell / ConvGRU.forward        /root/reference/backbone/convrnn.py:24-34, 62-88
     loss / target (driver side)          /root/reference/dpc/main.py:178-185, 213-217
     calc_topk_accuracy                   /root/reference/utils/utils.py:38-55
@@ -36,19 +37,32 @@ import torch.nn.functional as F
 # Architecture description (restated from backbone/resnet_2d3d.py:205-284, select_backbone.py:3-21)
 # --------------------------------------------------------------------------------------------
 NETWORKS = {
-    # name: (blocks per stage)   -- block types are [2d, 2d, 3d, 3d] for both (resnet_2d3d.py:274-284)
+    # name: (blocks per stage)   -- block types are [2d, 2d, 3d, 3d] for all of them (resnet_2d3d.py:274-308)
     'resnet18': (2, 2, 2, 2),
     'resnet34': (3, 4, 6, 3),
+    # Bottleneck networks (resnet_2d3d.py:119-202,286-308): restated and pinned here ahead of the product path,
+    # which still raises NotImplementedError for them
+    'resnet50': (3, 4, 6, 3),
+    'resnet101': (3, 4, 23, 3),
+    'resnet152': (3, 8, 36, 3),
+    'resnet200': (3, 24, 36, 3),
 }
+BOTTLENECK = ('resnet50', 'resnet101', 'resnet152', 'resnet200')
 STAGE_PLANES = (64, 128, 256, 256)      # layer4 narrowed to 256 (resnet_2d3d.py:222)
 STAGE_IS3D = (False, False, True, True)
-FEATURE_SIZE = 256                       # select_backbone.py:7,10
+FEATURE_SIZE = 256                       # select_backbone.py:7,10 (BasicBlock networks)
+
+
+def feature_size(network):
+    """select_backbone.py:4-10: 1024 for the Bottleneck networks (256 planes x expansion 4), 256 for r18 / r34"""
+    return 1024 if network in BOTTLENECK else FEATURE_SIZE
 
 
 def backbone_spec(network):
-    """List of blocks: dict(name, inplanes, planes, stride, is3d, downsample, final_relu)."""
+    """List of blocks: dict(name, block, inplanes, planes, outplanes, stride, is3d, downsample, final_relu)."""
     if network not in NETWORKS:
         raise IOError('model type is wrong')            # select_backbone.py:19
+    expansion = 4 if network in BOTTLENECK else 1       # resnet_2d3d.py:48,84,120,162
     spec = []
     inplanes = 64
     for si, nblocks in enumerate(NETWORKS[network]):
@@ -56,12 +70,13 @@ def backbone_spec(network):
         stride = 1 if si == 0 else 2
         for bi in range(nblocks):
             s = stride if bi == 0 else 1
-            ds = (bi == 0) and (s != 1 or inplanes != planes)      # resnet_2d3d.py:234
+            ds = (bi == 0) and (s != 1 or inplanes != planes * expansion)      # resnet_2d3d.py:234
             is_last = (si == 3 and bi == nblocks - 1)
-            spec.append(dict(name='layer%d.%d' % (si + 1, bi), inplanes=inplanes, planes=planes,
+            spec.append(dict(name='layer%d.%d' % (si + 1, bi), block='bottleneck' if expansion == 4 else 'basic',
+                             inplanes=inplanes, planes=planes, outplanes=planes * expansion,
                              stride=s, is3d=STAGE_IS3D[si], downsample=ds,
                              final_relu=not is_last))              # resnet_2d3d.py:249-252
-            inplanes = planes
+            inplanes = planes * expansion
     return spec
 
 
@@ -74,17 +89,28 @@ def param_shapes(network):
     for b in backbone_spec(network):
         p = 'backbone.' + b['name']
         k = (3, 3, 3) if b['is3d'] else (1, 3, 3)
-        sh[p + '.conv1.weight'] = (b['planes'], b['inplanes']) + k
-        sh[p + '.bn1.weight'] = (b['planes'],)
-        sh[p + '.bn1.bias'] = (b['planes'],)
-        sh[p + '.conv2.weight'] = (b['planes'], b['planes']) + k
-        sh[p + '.bn2.weight'] = (b['planes'],)
-        sh[p + '.bn2.bias'] = (b['planes'],)
+        if b['block'] == 'bottleneck':                              # resnet_2d3d.py:123-137,165-179
+            sh[p + '.conv1.weight'] = (b['planes'], b['inplanes'], 1, 1, 1)
+            sh[p + '.bn1.weight'] = (b['planes'],)
+            sh[p + '.bn1.bias'] = (b['planes'],)
+            sh[p + '.conv2.weight'] = (b['planes'], b['planes']) + k
+            sh[p + '.bn2.weight'] = (b['planes'],)
+            sh[p + '.bn2.bias'] = (b['planes'],)
+            sh[p + '.conv3.weight'] = (b['outplanes'], b['planes'], 1, 1, 1)
+            sh[p + '.bn3.weight'] = (b['outplanes'],)
+            sh[p + '.bn3.bias'] = (b['outplanes'],)
+        else:
+            sh[p + '.conv1.weight'] = (b['planes'], b['inplanes']) + k
+            sh[p + '.bn1.weight'] = (b['planes'],)
+            sh[p + '.bn1.bias'] = (b['planes'],)
+            sh[p + '.conv2.weight'] = (b['planes'], b['planes']) + k
+            sh[p + '.bn2.weight'] = (b['planes'],)
+            sh[p + '.bn2.bias'] = (b['planes'],)
         if b['downsample']:
-            sh[p + '.downsample.0.weight'] = (b['planes'], b['inplanes'], 1, 1, 1)
-            sh[p + '.downsample.1.weight'] = (b['planes'],)
-            sh[p + '.downsample.1.bias'] = (b['planes'],)
-    D = FEATURE_SIZE
+            sh[p + '.downsample.0.weight'] = (b['outplanes'], b['inplanes'], 1, 1, 1)
+            sh[p + '.downsample.1.weight'] = (b['outplanes'],)
+            sh[p + '.downsample.1.bias'] = (b['outplanes'],)
+    D = feature_size(network)
     for cell in ('agg.ConvGRUCell_00', 'agg.cell_list.0'):          # registered twice, convrnn.py:55-58
         for g in ('reset_gate', 'update_gate', 'out_gate'):
             sh['%s.%s.weight' % (cell, g)] = (D, 2 * D, 1, 1)
@@ -190,7 +216,7 @@ def _bn(x, sd, prefix, eps=1e-5):
 
 
 def backbone_forward(x, sd, network, prefix='backbone.', taps=None):
-    """x: [NB,3,T,H,W] -> [NB,256,T',H/32,W/32].  `taps` (dict) collects intermediates."""
+    """x: [NB,3,T,H,W] -> [NB,feature_size,T',H/32,W/32].  `taps` (dict) collects intermediates."""
     def tap(name, t):
         if taps is not None:
             taps[name] = t
@@ -208,10 +234,18 @@ def backbone_forward(x, sd, network, prefix='backbone.', taps=None):
         else:
             s1, pad = (1, b['stride'], b['stride']), (0, 1, 1)      # conv1x3x3, :23-31
             sds = (1, b['stride'], b['stride'])                     # customized_stride, :236-239
-        out = F.conv3d(x, sd[p + '.conv1.weight'], None, s1, pad)
-        out = F.relu(_bn(out, sd, p + '.bn1'))
-        out = F.conv3d(out, sd[p + '.conv2.weight'], None, 1, pad)
-        out = _bn(out, sd, p + '.bn2')
+        if b['block'] == 'bottleneck':                              # Bottleneck2d / 3d.forward, :139-158,181-200
+            out = F.conv3d(x, sd[p + '.conv1.weight'], None, 1, 0)
+            out = F.relu(_bn(out, sd, p + '.bn1'))
+            out = F.conv3d(out, sd[p + '.conv2.weight'], None, s1, pad)
+            out = F.relu(_bn(out, sd, p + '.bn2'))
+            out = F.conv3d(out, sd[p + '.conv3.weight'], None, 1, 0)
+            out = _bn(out, sd, p + '.bn3')
+        else:
+            out = F.conv3d(x, sd[p + '.conv1.weight'], None, s1, pad)
+            out = F.relu(_bn(out, sd, p + '.bn1'))
+            out = F.conv3d(out, sd[p + '.conv2.weight'], None, 1, pad)
+            out = _bn(out, sd, p + '.bn2')
         if b['downsample']:
             res = F.conv3d(x, sd[p + '.downsample.0.weight'], None, sds, 0)
             res = _bn(res, sd, p + '.downsample.1')
@@ -262,7 +296,7 @@ def dpc_forward(block, sd, network='resnet18', pred_step=3, dropout_masks=None, 
         if taps is not None:
             taps[name] = t
     B, N, C, SL, H, W = block.shape
-    D = FEATURE_SIZE
+    D = feature_size(network)
     last_duration = int(math.ceil(SL / 4))                          # model_3d.py:24
     L = int(math.ceil(H / 32))                                      # model_3d.py:25
     x = block.reshape(B * N, C, SL, H, W)
@@ -405,7 +439,7 @@ def lc_param_shapes(network, num_class=101):
         if b['downsample']:
             sh[p + '.downsample.0.weight'] = (b['planes'], b['inplanes'], 1, 1, 1)
             bn(p + '.downsample.1', b['planes'])
-    D = FEATURE_SIZE
+    D = feature_size(network)
     for cell in ('agg.ConvGRUCell_00', 'agg.cell_list.0'):
         for g in ('reset_gate', 'update_gate', 'out_gate'):
             sh['%s.%s.weight' % (cell, g)] = (D, 2 * D, 1, 1)

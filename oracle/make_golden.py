@@ -125,13 +125,15 @@ def main():
         ('r18_img128_b2', dict(network='resnet18', img=128, B=2, seed_w=12, seed_x=22)),
         ('r34_img64_b3', dict(network='resnet34', img=64, B=3, seed_w=13, seed_x=23)),
         ('r18_img96_b2_p2', dict(network='resnet18', img=96, B=2, seed_w=14, seed_x=24, pred_step=2)),
+        # Bottleneck network: pins the oracle's r50 restatement (the product path does not build r50+ yet)
+        ('r50_img64_b2', dict(network='resnet50', img=64, B=2, seed_w=15, seed_x=25)),
     ]
     for name, kw in cases:
         fx = make(**kw)
         path = os.path.join(outdir, name + '.pt')
         torch.save(fx, path)
         print(name, 'loss', fx['loss'], 'topk', fx['topk'], '%.1f KB' % (os.path.getsize(path) / 1e3))
-    init = {net: reference_init_checks(net) for net in ('resnet18', 'resnet34')}
+    init = {net: reference_init_checks(net) for net in ('resnet18', 'resnet34', 'resnet50')}
     torch.save(init, os.path.join(outdir, 'reference_init_seed0.pt'))
     print('init checks saved')
 

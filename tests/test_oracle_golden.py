@@ -6,12 +6,12 @@ import pytest
 import torch
 
 from oracle import dpc_oracle as O
-from tests.util import CASES, load_fixture, make_block, rel_err, check_sample
+from tests.util import CASES, ORACLE_ONLY_CASES, load_fixture, make_block, rel_err, check_sample
 
 TOL = 2e-5          # fp32 CPU vs fp32 CPU, same ATen ops, different composition (functional vs modules)
 
 
-@pytest.mark.parametrize('case', CASES)
+@pytest.mark.parametrize('case', CASES + ORACLE_ONLY_CASES)
 def test_forward_matches_reference(case):
     fx = load_fixture(case)
     sd = O.synthetic_state_dict(fx['network'], fx['seed_w'])
@@ -34,7 +34,7 @@ def test_forward_matches_reference(case):
     assert tk == pytest.approx(fx['topk'], abs=1e-6)
 
 
-@pytest.mark.parametrize('case', ['r18_img64_b2', 'r34_img64_b3'])
+@pytest.mark.parametrize('case', ['r18_img64_b2', 'r34_img64_b3', 'r50_img64_b2'])
 def test_grads_match_reference(case):
     fx = load_fixture(case)
     sd = O.synthetic_state_dict(fx['network'], fx['seed_w'])
@@ -60,7 +60,7 @@ def test_mask_closed_form_values():
     assert int((m == 0).sum()) == m.numel() - 36 - 72 - 324
 
 
-@pytest.mark.parametrize('net', ['resnet18', 'resnet34'])
+@pytest.mark.parametrize('net', ['resnet18', 'resnet34', 'resnet50'])
 def test_reference_init_restatement(net):
     """a16: kaiming-normal(fan_out) convs are bit-reproducible; the orthogonal GRU/pred weights go
     through LAPACK, so they are checked by property (W W^T = I) and, when the host matches, by value."""
@@ -79,7 +79,7 @@ def test_reference_init_restatement(net):
         else:
             assert float(v.abs().max()) == 0.0
     n_params = sum(v.numel() for k, v in sd.items() if not k.startswith('agg.ConvGRUCell_00'))
-    assert n_params == {'resnet18': 14583104, 'resnet34': 32947776}[net]
+    assert n_params == {'resnet18': 14583104, 'resnet34': 32947776, 'resnet50': 31956032}[net]    # SURVEY §8 a1 (+ r50 probe)
 
 
 def test_adam_matches_torch():
