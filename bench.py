@@ -170,10 +170,15 @@ def conv_family_flops(network, NB, T, H, W):
         To, Ho, Wo = e(Tc, k[0], s[0], p[0]), e(Hc, k[1], s[1], p[1]), e(Wc, k[2], s[2], p[2])
         rows = NB * To * Ho * Wo
         taps = k[0] * k[1] * k[2]
-        total += 2 * rows * b['planes'] * taps * b['inplanes']           # conv1
-        total += 2 * rows * b['planes'] * taps * b['planes']             # conv2
+        if b['block'] == 'bottleneck':                                     # 1x1x1 -> k (strided) -> 1x1x1
+            total += 2 * NB * Tc * Hc * Wc * b['planes'] * b['inplanes']
+            total += 2 * rows * b['planes'] * taps * b['planes']
+            total += 2 * rows * b['outplanes'] * b['planes']
+        else:
+            total += 2 * rows * b['planes'] * taps * b['inplanes']           # conv1
+            total += 2 * rows * b['planes'] * taps * b['planes']             # conv2
         if b['downsample']:
-            total += 2 * rows * b['planes'] * b['inplanes']
+            total += 2 * rows * b['outplanes'] * b['inplanes']
         Tc, Hc, Wc = To, Ho, Wo
     return 3 * total
 

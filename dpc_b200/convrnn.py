@@ -46,11 +46,11 @@ class ConvGRU(nn.Module):
 
     def forward(self, x, hidden_state=None):
         """x [B,T,C,H,W] -> (layer_output [B,T,C,H,W], last_state [B,1,C,H,W])  (convrnn.py:62-88).
-        Built for the configuration the reference uses: kernel_size 1, one layer, input == hidden == 256."""
+        Built for the configuration the reference uses: kernel_size 1, one layer, input == hidden (256 / 1024)."""
         from . import engine
         if self.kernel_size != 1 or self.num_layers != 1 or self.input_size != self.hidden_size \
-                or self.hidden_size != engine.FEATURE_SIZE:
-            raise NotImplementedError('ConvGRU CUDA path: kernel_size=1, num_layers=1, input=hidden=%d only' % engine.FEATURE_SIZE)
+                or self.hidden_size % 64 != 0:
+            raise NotImplementedError('ConvGRU CUDA path: kernel_size=1, num_layers=1, input=hidden (a multiple of 64) only')
         if not x.is_cuda:
             raise RuntimeError('dpc_b200 has no CPU path: input must be a CUDA tensor')
         B, T, C, H, W = x.shape

@@ -296,6 +296,8 @@ def backbone_param_names(network):
         p = b['name']
         names += [p + '.conv1.weight', p + '.bn1.weight', p + '.bn1.bias',
                   p + '.conv2.weight', p + '.bn2.weight', p + '.bn2.bias']
+        if b['block'] == 'bottleneck':
+            names += [p + '.conv3.weight', p + '.bn3.weight', p + '.bn3.bias']
         if b['downsample']:
             names += [p + '.downsample.0.weight', p + '.downsample.1.weight', p + '.downsample.1.bias']
     return names
@@ -384,6 +386,47 @@ def backbone_forward(network, x, P, need_ctx=True, bn_state=None, training=True)
         else:
             k, pad = (1, 3, 3), (0, 1, 1)
             s1 = (1, b['stride'], b['stride'])
+        want_rows = (not tc) or last                 # the last block's output feeds the head as fp32 rows
+        want_planes = tc and not last
+        if b['block'] == 'bottleneck':
+            # Bottleneck2d / 3d (resnet_2d3d.py:119-202): 1x1x1 -> k (carries the stride) -> 1x1x1 (x4 channels)
+            one, nopad = (1, 1, 1), (0, 0, 0)
+            c1 = Site(NB, dims, b['inplanes'], b['planes'], one, one, nopad)
+            c1.pack(P[p + '.conv1.weight'], st)
+            y1, m1, r1 = _conv_bn(c1, cur_op, p + '.bn1', bn_state, training, st)
+            a1, a1_pl = _bn_apply(y1, m1, r1, P[p + '.bn1.weight'], P[p + '.bn1.bias'], True, c1.rows_out, c1.Co, st,
+                                  want_rows=not tc, want_planes=tc)
+            a1_op = a1_pl if tc else a1
+            c2 = Site(NB, c1.dims_out, b['planes'], b['planes'], k, s1, pad)
+            c2.pack(P[p + '.conv2.weight'], st)
+            y2, m2, r2 = _conv_bn(c2, a1_op, p + '.bn2', bn_state, training, st)
+            a2, a2_pl = _bn_apply(y2, m2, r2, P[p + '.bn2.weight'], P[p + '.bn2.bias'], True, c2.rows_out, c2.Co, st,
+                                  want_rows=not tc, want_planes=tc)
+            a2_op = a2_pl if tc else a2
+            c3 = Site(NB, c2.dims_out, b['planes'], b['outplanes'], one, one, nopad)
+            c3.pack(P[p + '.conv3.weight'], st)
+            y3, m3, r3 = _conv_bn(c3, a2_op, p + '.bn3', bn_state, training, st)
+            rec = dict(spec=b, c1=c1, c2=c2, c3=c3, xin_op=cur_op, y1=y1, m1=m1, r1=r1, a1=a1, a1_op=a1_op,
+                       y2=y2, m2=m2, r2=r2, a2=a2, a2_op=a2_op, y3=y3, m3=m3, r3=r3, tc=tc)
+            if b['downsample']:
+                cd = Site(NB, dims, b['inplanes'], b['outplanes'], one, s1, nopad)
+                cd.pack(P[p + '.downsample.0.weight'], st)
+                yd, md, rd = _conv_bn(cd, cur_op, p + '.downsample.1', bn_state, training, st)
+                out, out_pl = _bn_apply(y3, m3, r3, P[p + '.bn3.weight'], P[p + '.bn3.bias'], b['final_relu'],
+                                        c3.rows_out, c3.Co, st, res=yd,
+                                        rbn=(md, rd, P[p + '.downsample.1.weight'], P[p + '.downsample.1.bias']),
+                                        want_rows=want_rows, want_planes=want_planes)
+                rec.update(cd=cd, yd=yd, md=md, rd=rd)
+            else:
+                out, out_pl = _bn_apply(y3, m3, r3, P[p + '.bn3.weight'], P[p + '.bn3.bias'], b['final_relu'],
+                                        c3.rows_out, c3.Co, st, res=cur, res_planes=cur_op if tc else None,
+                                        want_rows=want_rows, want_planes=want_planes)
+            rec['out'], rec['out_hi'] = out, (out_pl[0] if out_pl else None)
+            if need_ctx:
+                ctx['blocks'].append(rec)
+            cur, dims, C = out, c3.dims_out, b['outplanes']
+            cur_op = out_pl if tc else out
+            continue
         c1 = Site(NB, dims, b['inplanes'], b['planes'], k, s1, pad)
         c1.pack(P[p + '.conv1.weight'], st)
         y1, m1, r1 = _conv_bn(c1, cur_op, p + '.bn1', bn_state, training, st)
@@ -396,8 +439,6 @@ def backbone_forward(network, x, P, need_ctx=True, bn_state=None, training=True)
         y2, m2, r2 = _conv_bn(c2, a1_op, p + '.bn2', bn_state, training, st)
         rec = dict(spec=b, c1=c1, c2=c2, xin_op=cur_op, y1=y1, m1=m1, r1=r1, a1=a1, a1_op=a1_op,
                    y2=y2, m2=m2, r2=r2, tc=tc)
-        want_rows = (not tc) or last                 # the last block's output feeds the head as fp32 rows
-        want_planes = tc and not last
         if b['downsample']:
             cd = Site(NB, dims, b['inplanes'], b['planes'], (1, 1, 1), s1, (0, 0, 0))
             cd.pack(P[p + '.downsample.0.weight'], st)
@@ -489,6 +530,47 @@ def _backbone_backward(ctx, dout, P, side):
         tc = rec['tc']
         kw = dict(want_rows=not tc, want_planes=tc)          # conv-operand format of the dy tensors
         op = (lambda rows, planes: planes) if tc else (lambda rows, planes: rows)
+        if b['block'] == 'bottleneck':
+            c3 = rec['c3']
+            dy3r, dy3p, G[p + '.bn3.weight'], G[p + '.bn3.bias'], g = _bn_bwd(
+                dout, rec['out'], relu, rec['y3'], rec['m3'], rec['r3'], P[p + '.bn3.weight'],
+                c3.rows_out, c3.Co, st, want_g=not has_ds, out_hi=rec['out_hi'], **kw)
+            dy3 = op(dy3r, dy3p)
+            if has_ds:
+                cd = rec['cd']
+                dydr, dydp, G[p + '.downsample.1.weight'], G[p + '.downsample.1.bias'], _ = _bn_bwd(
+                    dout, rec['out'], relu, rec['yd'], rec['md'], rec['rd'], P[p + '.downsample.1.weight'],
+                    cd.rows_out, cd.Co, st, out_hi=rec['out_hi'], **kw)
+                dyd = op(dydr, dydp)
+            del dout
+            G[p + '.conv3.weight'] = _wgrad_async(c3, rec['a2_op'], dy3, main, side)
+            da2 = c3.dgrad(dy3, st)
+            del dy3, dy3r, dy3p
+            dy2r, dy2p, G[p + '.bn2.weight'], G[p + '.bn2.bias'], _ = _bn_bwd(
+                da2, rec['a2'], True, rec['y2'], rec['m2'], rec['r2'], P[p + '.bn2.weight'],
+                c2.rows_out, c2.Co, st, out_hi=(rec['a2_op'][0] if tc else None), **kw)
+            dy2 = op(dy2r, dy2p)
+            del da2
+            G[p + '.conv2.weight'] = _wgrad_async(c2, rec['a1_op'], dy2, main, side)
+            da1 = c2.dgrad(dy2, st)
+            del dy2, dy2r, dy2p
+            dy1r, dy1p, G[p + '.bn1.weight'], G[p + '.bn1.bias'], _ = _bn_bwd(
+                da1, rec['a1'], True, rec['y1'], rec['m1'], rec['r1'], P[p + '.bn1.weight'],
+                c1.rows_out, c1.Co, st, out_hi=(rec['a1_op'][0] if tc else None), **kw)
+            dy1 = op(dy1r, dy1p)
+            del da1
+            G[p + '.conv1.weight'] = _wgrad_async(c1, rec['xin_op'], dy1, main, side)
+            if has_ds:
+                dx = c1.dgrad(dy1, st)
+                cd.dgrad(dyd, st, dx=dx)
+                G[p + '.downsample.0.weight'] = _wgrad_async(cd, rec['xin_op'], dyd, main, side)
+                del dyd, dydr, dydp
+            else:
+                dx = c1.dgrad(dy1, st, dx=g)          # dx = g + dgrad
+            del dy1, dy1r, dy1p
+            dout = dx
+            rec.clear()
+            continue
         dy2r, dy2p, G[p + '.bn2.weight'], G[p + '.bn2.bias'], g = _bn_bwd(
             dout, rec['out'], relu, rec['y2'], rec['m2'], rec['r2'], P[p + '.bn2.weight'],
             c2.rows_out, c2.Co, st, want_g=not has_ds, out_hi=rec['out_hi'], ws=ws_out, **kw)
@@ -520,7 +602,8 @@ def _backbone_backward(ctx, dout, P, side):
             cd.dgrad(dyd, st, dx=dx)
             G[p + '.downsample.0.weight'] = _wgrad_async(cd, rec['xin_op'], dyd, main, side)
             del dyd, dydr, dydp
-        elif tc and FUSE_BN_REDUCE and bi > 0 and c1.stride1 and blocks[bi - 1].get('out_hi') is not None:
+        elif tc and FUSE_BN_REDUCE and bi > 0 and c1.stride1 and blocks[bi - 1].get('out_hi') is not None \
+                and blocks[bi - 1]['spec']['block'] == 'basic':
             # dx = g + dgrad is the previous block's output gradient: reduce that block's bn2 sums here
             prev = blocks[bi - 1]
             dx, ws_out = c1.dgrad_bnred(dy1, st, prev['out_hi'] if prev['spec']['final_relu'] else None,
@@ -648,7 +731,7 @@ def head_forward(z4, dims, B, N, pred_step, P, dropout_p=0.0, seed=0, need_ctx=T
     L = lib()
     st = _stream()
     To, Lh, Lw = dims
-    S, D = Lh * Lw, FEATURE_SIZE
+    S, D = Lh * Lw, z4.shape[1]              # feature size: 256 (r18 / r34) or 1024 (Bottleneck networks)
     NB = B * N
     Tagg = N - pred_step
     R = B * S
@@ -784,7 +867,7 @@ def head_backward(ctx, dscore, P):
 def gru_sequence_forward(X_all, h0, P, R, T, dropout_p, seed):
     """X_all rows [T*R, D] (step-major); h0 [R, D] or None.  Returns (H_all [T*R, D] post-dropout states, steps)."""
     st = _stream()
-    D = FEATURE_SIZE
+    D = X_all.shape[1]
     gru = _Gru(P, D, st)
     XP = gru.xproj(X_all, T * R)
     h = h0 if h0 is not None else torch.zeros((R, D), dtype=torch.float32, device=X_all.device)
@@ -801,7 +884,7 @@ def gru_sequence_backward(steps, X_all, dH_all, dh_last, P, R, T, G):
     """dH_all [T*R, D] or None: gradient w.r.t. every step's output; dh_last [R, D] or None: extra gradient on the
     final state.  Accumulates weight grads into G.  Returns (dX_all [T*R, D], dh0)."""
     st = _stream()
-    D = FEATURE_SIZE
+    D = X_all.shape[1]
     gru = _Gru(P, D, st)
     L = lib()
     dX_all = _empty((T * R, D), X_all)
@@ -825,7 +908,7 @@ def gru_sequence_backward(steps, X_all, dH_all, dh_last, P, R, T, G):
 
 
 def _new_head_grads(P, dev):
-    D = FEATURE_SIZE
+    D = P['agg.cell_list.0.update_gate.bias'].numel()
     G = {n: torch.zeros_like(P[n]) for n in HEAD_PARAM_NAMES[:6]}
     G['_bzr'] = torch.zeros(2 * D, dtype=torch.float32, device=dev)
     G['agg.cell_list.0.update_gate.bias'] = G['_bzr'][:D]
@@ -841,7 +924,7 @@ def lc_head_forward(z4, dims, B, N, P, final_bn_state, training, gru_p, fc_p, se
     L = lib()
     st = _stream()
     To, Lh, Lw = dims
-    S, D = Lh * Lw, FEATURE_SIZE
+    S, D = Lh * Lw, z4.shape[1]
     NB, R = B * N, B * S
     feat = _empty((NB * S, D), z4)
     L.relu_pool_fwd(ptr(z4), ptr(feat), NB, To, S * D, st)                   # ReLU, then temporal mean

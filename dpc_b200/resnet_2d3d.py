@@ -11,9 +11,10 @@ import torch.nn as nn
 from torch.autograd.function import once_differentiable
 
 from . import engine
-from .arch import backbone_spec
+from .arch import backbone_spec, NETWORKS
 
-__all__ = ['ResNet2d3d_full', 'BasicBlock2d', 'BasicBlock3d', 'resnet18_2d3d_full', 'resnet34_2d3d_full',
+__all__ = ['ResNet2d3d_full', 'BasicBlock2d', 'BasicBlock3d', 'Bottleneck2d', 'Bottleneck3d', 'resnet18_2d3d_full',
+           'resnet34_2d3d_full',
            'resnet50_2d3d_full', 'resnet101_2d3d_full', 'resnet152_2d3d_full', 'resnet200_2d3d_full',
            'neq_load_customized']
 
@@ -63,8 +64,38 @@ class BasicBlock2d(_BasicBlock):                                   # resnet_2d3d
     _conv = staticmethod(conv1x3x3)
 
 
+class _Bottleneck(nn.Module):
+    expansion = 4
+    _conv = None
+
+    def __init__(self, inplanes, planes, stride=1, downsample=None, track_running_stats=True,
+                 use_final_relu=True):
+        super().__init__()
+        self.use_final_relu = use_final_relu
+        self.conv1 = nn.Conv3d(inplanes, planes, kernel_size=1, bias=False)
+        self.bn1 = nn.BatchNorm3d(planes, track_running_stats=track_running_stats)
+        self.conv2 = type(self)._conv(planes, planes, stride, bias=False)
+        self.bn2 = nn.BatchNorm3d(planes, track_running_stats=track_running_stats)
+        self.conv3 = nn.Conv3d(planes, planes * 4, kernel_size=1, bias=False)
+        self.bn3 = nn.BatchNorm3d(planes * 4, track_running_stats=track_running_stats)
+        self.relu = nn.ReLU(inplace=True)
+        self.downsample = downsample
+        self.stride = stride
+
+    def forward(self, x):
+        raise RuntimeError('blocks are parameter holders; call the ResNet2d3d_full module (CUDA path)')
+
+
+class Bottleneck3d(_Bottleneck):                                   # resnet_2d3d.py:119-158
+    _conv = staticmethod(conv3x3x3)
+
+
+class Bottleneck2d(_Bottleneck):                                   # resnet_2d3d.py:161-202
+    _conv = staticmethod(conv1x3x3)
+
+
 class _BackboneFn(torch.autograd.Function):
-    """x [NB,3,T,H,W] -> channels-last feature rows [NB*To*Ho*Wo, 256]"""
+    """x [NB,3,T,H,W] -> channels-last feature rows [NB*To*Ho*Wo, feature_size]"""
 
     @staticmethod
     def forward(ctx, x, network, names, need, *params):
@@ -97,11 +128,12 @@ class ResNet2d3d_full(nn.Module):                                  # resnet_2d3d
         self.maxpool = nn.MaxPool3d(kernel_size=(1, 3, 3), stride=(1, 2, 2), padding=(0, 1, 1))
         if not isinstance(block, list):
             block = [block] * 4
-        for b in block:
-            if b not in (BasicBlock2d, BasicBlock3d):
-                raise NotImplementedError('Bottleneck blocks (resnet50+) are outside the B200 hot-path scope')
-        if block != [BasicBlock2d, BasicBlock2d, BasicBlock3d, BasicBlock3d]:
-            raise NotImplementedError('only the [2d,2d,3d,3d] BasicBlock layout (r18/r34) is built')
+        if block == [BasicBlock2d, BasicBlock2d, BasicBlock3d, BasicBlock3d]:
+            kind = 'basic'
+        elif block == [Bottleneck2d, Bottleneck2d, Bottleneck3d, Bottleneck3d]:
+            kind = 'bottleneck'
+        else:
+            raise NotImplementedError('only the [2d,2d,3d,3d] BasicBlock / Bottleneck layouts of the reference are built')
         self.layer1 = self._make_layer(block[0], 64, layers[0])
         self.layer2 = self._make_layer(block[1], 128, layers[1], stride=2)
         self.layer3 = self._make_layer(block[2], 256, layers[2], stride=2)
@@ -115,9 +147,9 @@ class ResNet2d3d_full(nn.Module):                                  # resnet_2d3d
                 m.weight.data.fill_(1)
                 m.bias.data.zero_()
         layers = tuple(layers)
-        self.network = {(2, 2, 2, 2): 'resnet18', (3, 4, 6, 3): 'resnet34'}.get(layers)
+        self.network = {v: k for k, v in NETWORKS.items()}.get((layers, kind))
         if self.network is None:
-            raise NotImplementedError('layer counts %s: only resnet18/resnet34 are built' % (layers,))
+            raise NotImplementedError('layer counts %s (%s blocks) are not one of the reference networks' % (layers, kind))
         self._names = engine.backbone_param_names(self.network)
         assert [b['downsample'] for b in backbone_spec(self.network)] == \
             [blk.downsample is not None for l in (self.layer1, self.layer2, self.layer3, self.layer4) for blk in l]
@@ -125,7 +157,7 @@ class ResNet2d3d_full(nn.Module):                                  # resnet_2d3d
     def _make_layer(self, block, planes, blocks, stride=1, is_final=False):   # resnet_2d3d.py:232-257
         downsample = None
         if stride != 1 or self.inplanes != planes * block.expansion:
-            customized_stride = (1, stride, stride) if block is BasicBlock2d else stride
+            customized_stride = (1, stride, stride) if block in (BasicBlock2d, Bottleneck2d) else stride
             downsample = nn.Sequential(
                 nn.Conv3d(self.inplanes, planes * block.expansion, kernel_size=1, stride=customized_stride, bias=False),
                 nn.BatchNorm3d(planes * block.expansion, track_running_stats=self.track_running_stats))
@@ -152,7 +184,7 @@ class ResNet2d3d_full(nn.Module):                                  # resnet_2d3d
         return T, H, W
 
     def forward_rows(self, x):
-        """x [NB,3,T,H,W] -> (rows [NB*To*Ho*Wo, 256] channels-last, (To,Ho,Wo))"""
+        """x [NB,3,T,H,W] -> (rows [NB*To*Ho*Wo, feature_size] channels-last, (To,Ho,Wo))"""
         if self.track_running_stats:
             raise NotImplementedError('track_running_stats=True (eval/LC) is a SURVEY.md §8(f) "next" row')
         if x.dim() != 5 or x.shape[1] != 3:
@@ -180,17 +212,16 @@ def resnet34_2d3d_full(**kwargs):                                  # resnet_2d3d
     return ResNet2d3d_full([BasicBlock2d, BasicBlock2d, BasicBlock3d, BasicBlock3d], [3, 4, 6, 3], **kwargs)
 
 
-def _bottleneck(name):
+def _bottleneck_factory(layers):
     def f(**kwargs):
-        raise NotImplementedError('%s (Bottleneck2d/3d, resnet_2d3d.py:286-308) is outside the hot-path scope' % name)
-    f.__name__ = name
+        return ResNet2d3d_full([Bottleneck2d, Bottleneck2d, Bottleneck3d, Bottleneck3d], list(layers), **kwargs)
     return f
 
 
-resnet50_2d3d_full = _bottleneck('resnet50_2d3d_full')
-resnet101_2d3d_full = _bottleneck('resnet101_2d3d_full')
-resnet152_2d3d_full = _bottleneck('resnet152_2d3d_full')
-resnet200_2d3d_full = _bottleneck('resnet200_2d3d_full')
+resnet50_2d3d_full = _bottleneck_factory((3, 4, 6, 3))             # resnet_2d3d.py:286-290
+resnet101_2d3d_full = _bottleneck_factory((3, 4, 23, 3))           # :292-296
+resnet152_2d3d_full = _bottleneck_factory((3, 8, 36, 3))           # :298-302
+resnet200_2d3d_full = _bottleneck_factory((3, 24, 36, 3))          # :304-308
 
 
 def neq_load_customized(model, pretrained_dict):

@@ -18,7 +18,7 @@ def _quiet(fn, *a, **k):
         return fn(*a, **k)
 
 
-@pytest.mark.parametrize('net', ['resnet18', 'resnet34'])
+@pytest.mark.parametrize('net', ['resnet18', 'resnet34', 'resnet50'])
 def test_module_surface_matches_reference_state_dict(net):
     import dpc_b200
     torch.manual_seed(0)
@@ -35,7 +35,8 @@ def test_module_surface_matches_reference_state_dict(net):
         if k.startswith('backbone.'):
             assert torch.equal(sd[k], ref[k]), k
     assert m.last_duration == 2 and m.last_size == 4
-    assert m.param == {'feature_size': 256, 'num_layers': 1, 'hidden_size': 256}
+    fs = 1024 if net == 'resnet50' else 256                          # select_backbone.py:4-10
+    assert m.param == {'feature_size': fs, 'num_layers': 1, 'hidden_size': fs}
     # loads a reference-style checkpoint
     m.load_state_dict(O.synthetic_state_dict(net, 3), strict=True)
     m.reset_mask()
@@ -50,8 +51,8 @@ def test_select_resnet_contract():
     assert model.out_dims(5, 128, 128) == (2, 4, 4) and model.out_dims(5, 224, 224) == (2, 7, 7)
     with pytest.raises(IOError):
         dpc_b200.select_resnet('vgg')
-    with pytest.raises(NotImplementedError):
-        dpc_b200.select_resnet('resnet50')
+    m50, p50 = dpc_b200.select_resnet('resnet50', track_running_stats=False)
+    assert p50 == {'feature_size': 1024} and m50.network == 'resnet50'
     part = {k: torch.zeros_like(v) for k, v in model.state_dict().items() if 'layer1' in k}
     part['not.a.key'] = torch.zeros(1)
     _quiet(neq_load_customized, model, part)
@@ -61,12 +62,11 @@ def test_select_resnet_contract():
 
 def test_arch_tables_agree_with_oracle():
     from dpc_b200.arch import backbone_spec
-    for net in ('resnet18', 'resnet34'):
+    for net in ('resnet18', 'resnet34', 'resnet50', 'resnet101'):
         a, b = backbone_spec(net), O.backbone_spec(net)
         assert len(a) == len(b)
         for x, y in zip(a, b):
-            assert all(x[k] == y[k] for k in y if k in x)       # the oracle spec also carries block / outplanes (r50+)
-            assert y['block'] == 'basic' and y['outplanes'] == x['planes']
+            assert all(x[k] == y[k] for k in y)
 
 
 def test_shard_batch():

@@ -2,8 +2,8 @@ import os
 import torch
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
-CASES = ['r18_img64_b2', 'r18_img128_b2', 'r34_img64_b3', 'r18_img96_b2_p2']
-ORACLE_ONLY_CASES = ['r50_img64_b2']        # Bottleneck network: oracle pinned, product path not built yet
+CASES = ['r18_img64_b2', 'r18_img128_b2', 'r34_img64_b3', 'r18_img96_b2_p2', 'r50_img64_b2']
+ORACLE_ONLY_CASES = []
 
 
 def load_fixture(name):
