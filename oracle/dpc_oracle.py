@@ -422,6 +422,8 @@ def cpu_train_step_time(network='resnet18', img=128, batch=4, steps=3, warmup=1,
 # --------------------------------------------------------------------------------------------
 def lc_param_shapes(network, num_class=101):
     """parameters AND buffers of LC in state_dict order (track_running_stats=True everywhere)"""
+    if network in BOTTLENECK:
+        raise NotImplementedError('the LC restatement covers the BasicBlock networks (resnet18 / resnet34) only')
     sh = OrderedDict()
 
     def bn(prefix, c):
@@ -492,7 +494,7 @@ def _bn_rs(x, sd, prefix, training, momentum=0.1, eps=1e-5, new_stats=None):
 def lc_forward(block, sd, network='resnet18', training=False, new_stats=None):
     """LC.forward with dropout off (eval, or train with p = 0).  Returns (output [B,1,num_class], context [B,1,D])."""
     B, N, C, SL, H, W = block.shape
-    D = FEATURE_SIZE
+    D = feature_size(network)
     last_duration = int(math.ceil(SL / 4))
     L = int(math.ceil(H / 32))
     bn = lambda x, p: _bn_rs(x, sd, p, training, new_stats=new_stats)
