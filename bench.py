@@ -38,6 +38,8 @@ def parse():
     ap.add_argument('--pred_step', type=int, default=3)
     ap.add_argument('--no_cpu_baseline', action='store_true')
     ap.add_argument('--no_e2e', action='store_true')
+    ap.add_argument('--no_stock', action='store_true', help='skip the stock PyTorch-CUDA leg')
+    ap.add_argument('--stock_steps', type=int, default=4)
     return ap.parse_args()
 
 
@@ -132,28 +134,100 @@ class ClockSampler:
 
 
 # ---------------------------------------------------------------------------------------------
+def ref_sample_batch(a):
+    """clips per CPU step of the reference arm: BASELINE config 1 (4 clips at R18 / 128^2, ~1 s per step on 32 host
+    threads), scaled down for the heavier configs so that `--steps K --warmup W` still ends within a few minutes"""
+    cost = (a.img_dim / 128.0) ** 2 * (7.1 if a.net == 'resnet34' else 1.0 if a.net == 'resnet18' else 4.0)
+    return max(1, min(4, int(round(4 / cost))))
+
+
+def cpu_reference_step(a):
+    """-> (step fn, kind, impl description) for the CPU arms: the unmodified reference modules staged in baseline/_ref
+    (oracle/make_ref.py) driven by main.py's own loop lines, else the oracle port"""
+    import torch
+    from oracle import ref_harness as H
+    step = H.reference_step(a.net, a.img_dim, a.pred_step, torch.device('cpu'))
+    if step is not None:
+        return step, 'reference', 'unmodified reference modules (baseline/_ref) + main.py loop lines, torch CPU fp32'
+    return H.port_step(a.net, a.img_dim, a.pred_step, torch.device('cpu')), 'port', 'oracle port (oracle/dpc_oracle.py), torch CPU fp32'
+
+
+def time_cpu_steps(a, steps, warmup):
+    """-> (seconds per step, clips per step, kind, impl, threads): fwd + CE + top-k + bwd + Adam on the host cores"""
+    import torch
+    torch.set_num_threads(cpu_threads())
+    bs = ref_sample_batch(a)
+    step, kind, impl = cpu_reference_step(a)
+    g = torch.Generator().manual_seed(1234)
+    x = torch.randn(bs, 8, 3, 5, a.img_dim, a.img_dim, generator=g)
+    for _ in range(warmup):
+        step(x)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step(x)
+    return (time.perf_counter() - t0) / steps, bs, kind, impl, torch.get_num_threads()
+
+
 def run_reference(a, rank, world):
-    """the reference's algorithm on the host cores: the oracle port (oracle/dpc_oracle.py; the
-    reference itself is Python over ATen and cannot travel to the GPU box).  Bounded sample: B=4
-    clips per step (BASELINE config 1)."""
+    """`--impl reference`: the reference's own CPU implementation of the path on this box's host cores.  Runs EXACTLY
+    the requested W warm-up + K timed steps; each step is a bounded sample of the workload (`ref_sample_batch` clips
+    instead of batch_per_gpu -- stated in config.reference_sample), so the line's steps / ms_per_step are the real ones."""
     if rank != 0:
         return
-    import torch
-    from oracle import dpc_oracle as O
-    torch.set_num_threads(cpu_threads())
-    bs = 4
-    t = O.cpu_train_step_time(a.net, a.img_dim, batch=bs, steps=max(1, min(a.steps, 5)), warmup=1)
+    t, bs, kind, impl, threads = time_cpu_steps(a, a.steps, a.warmup)
     v = bs / t
     cfg = workload(a, world)
+    cfg['reference_sample'] = {'clips_per_step': bs, 'note': 'each timed step is fwd + CE + top-k + bwd + Adam over %d clips '
+                               '(not batch_per_gpu) on %d host threads; value = clips_per_step / seconds per step' % (bs, threads)}
     line = {'impl': 'reference', 'metric': METRIC, 'value': v, 'unit': 'clips/s', 'n_gpus': a.gpus,
             'steps': a.steps, 'warmup': a.warmup, 'ms_per_step': t * 1e3, 'higher_is_better': True,
             'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic', 'config': cfg,
-            'cpu_baseline': {'value': v, 'unit': 'clips/s', 'cores': torch.get_num_threads(), 'kind': 'port',
-                             'sample': 'median of %d train steps (fwd+CE+bwd+Adam) at batch %d clips, %s img %d, '
-                                       'torch CPU fp32' % (max(1, min(a.steps, 5)), bs, a.net, a.img_dim)},
+            'cpu_baseline': {'value': v, 'unit': 'clips/s', 'cores': threads, 'kind': kind,
+                             'sample': '%d timed train steps (fwd+CE+top-k+bwd+Adam) of %d clips each, %s img %d, %s'
+                                       % (a.steps, bs, a.net, a.img_dim, impl)},
             'e2e': {'value': v, 'unit': 'clips/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
             'gpu_launches': 0}
     print(json.dumps(line))
+
+
+def run_stock_cuda(a, world, steps, warmup=2):
+    """The reference's real GPU path ("stock PyTorch-CUDA", north_star's 10x denominator): unmodified reference modules
+    under nn.DataParallel over `world` GPUs (main.py:65), cudnn.benchmark (main.py:25), torch's default TF32 convs,
+    Adam, the driver's loss / top-k lines -- global batch world x batch_per_gpu on device 0, device-timed.
+    Runs in THIS process (rank 0) after our arm has released its memory."""
+    import torch
+    from oracle import ref_harness as H
+    torch.backends.cudnn.benchmark = True
+    dev = torch.device('cuda', 0)
+    ids = list(range(world))
+    step = H.reference_step(a.net, a.img_dim, a.pred_step, dev, device_ids=ids)
+    impl = 'unmodified reference modules (baseline/_ref) under nn.DataParallel(%d), cudnn.benchmark, TF32 convs' % world
+    if step is None:
+        if world > 1:
+            return {'unavailable': 'baseline/_ref not staged and the oracle port has no DataParallel wrapper'}
+        step = H.port_step(a.net, a.img_dim, a.pred_step, dev)
+        impl = 'oracle port on CUDA (reference op sequence), cudnn.benchmark, TF32 convs'
+    B = a.batch_size * world
+    g = torch.Generator().manual_seed(4321)
+    x = torch.randn(B, 8, 3, 5, a.img_dim, a.img_dim, generator=g).to(dev)
+    for _ in range(warmup):
+        step(x)
+    for d in ids:
+        torch.cuda.synchronize(d)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    e0.record()
+    for _ in range(steps):
+        loss = step(x)
+        _ = loss.item()                                             # main.py:224: losses.update(loss.item(), B)
+    e1.record()
+    for d in ids:
+        torch.cuda.synchronize(d)
+    wall = (time.perf_counter() - t0) * 1e3 / steps
+    ms = e0.elapsed_time(e1) / steps
+    return {'clips_s': B / (ms / 1e3), 'ms_per_step': ms, 'wall_ms_per_step': wall, 'steps': steps, 'warmup': warmup,
+            'global_batch': B, 'n_gpus': world, 'impl': impl, 'loss': float(loss),
+            'peak_mem_gb': torch.cuda.max_memory_allocated(dev) / 1e9}
 
 
 def conv_family_flops(network, NB, T, H, W):
@@ -190,8 +264,11 @@ def run_b200(a, rank, local_rank, world):
     from dpc_b200 import engine
     torch.cuda.set_device(local_rank)
     dev = torch.device('cuda', local_rank)
+    gloo = None
     if world > 1:
+        import datetime
         dist.init_process_group('nccl', device_id=dev)
+        gloo = dist.new_group(backend='gloo', timeout=datetime.timedelta(minutes=30))   # host-side waits (stock leg)
     torch.manual_seed(0)
     with contextlib.redirect_stdout(io.StringIO()):
         model = dpc_b200.DPC_RNN(a.img_dim, num_seq=8, seq_len=5, pred_step=a.pred_step, network=a.net)
@@ -237,7 +314,14 @@ def run_b200(a, rank, local_rank, world):
         loss = step(x_dev)
     e1.record()
     barrier()
-    ms_total = max_over_ranks(e0.elapsed_time(e1))
+    ms_local = e0.elapsed_time(e1)
+    ms_total = max_over_ranks(ms_local)
+    rank_ms = None
+    if world > 1:                                                    # every rank's own device time per step
+        t = torch.tensor([ms_local / a.steps], device=dev, dtype=torch.float64)
+        allt = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(allt, t)
+        rank_ms = [round(float(v[0]), 3) for v in allt]
     launches = L.launch_count() - n0
     clocks = sampler.stop() if sampler else None
     ms_step = ms_total / a.steps
@@ -293,6 +377,7 @@ def run_b200(a, rank, local_rank, world):
         step(x_dev)
         engine.set_timer(None)
         tot = timer.totals()
+        allreduce_ms = tot.pop('allreduce', (0, None))[1]
         fam = {k: {'calls': c, 'ms': round(t, 3)} for k, (c, t) in sorted(tot.items(), key=lambda kv: -kv[1][1])}
         conv_ms = sum(t for k, (c, t) in tot.items() if k in ('conv_fwd', 'conv_dgrad', 'conv_wgrad'))
         flops = conv_family_flops(a.net, B * 8, 5, a.img_dim, a.img_dim)
@@ -325,22 +410,40 @@ def run_b200(a, rank, local_rank, world):
         step(x_dev)                                                  # keep the collective count equal
     barrier()
 
+    # ---- stock PyTorch-CUDA leg (the reference's own GPU path), after our arm released its memory ----------
+    stock = None
+    if not a.no_stock:
+        import gc
+        del model, trainer, crit, x_dev, step
+        if not a.no_e2e:
+            del bufs
+        gc.collect()
+        torch.cuda.empty_cache()
+        barrier()
+        if rank == 0:
+            try:
+                stock = run_stock_cuda(a, world, steps=max(1, min(a.stock_steps, a.steps)))
+            except Exception as exc:                                 # report, never hide: the leg is evidence, not product
+                stock = {'error': '%s: %s' % (type(exc).__name__, str(exc)[:300])}
+            torch.cuda.empty_cache()
+        if world > 1:
+            dist.barrier(group=gloo)                                 # host-side wait: no kernel spinning on the idle GPUs
+
     cpu = None
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
-        from oracle import dpc_oracle as O
-        torch.set_num_threads(cpu_threads())
-        bs = 4
-        t = O.cpu_train_step_time(a.net, a.img_dim, batch=bs, steps=3, warmup=1)
-        cpu = {'value': bs / t, 'unit': 'clips/s', 'cores': torch.get_num_threads(), 'kind': 'port',
-               'sample': 'median of 3 train steps (fwd+CE+bwd+Adam) at batch %d clips (BASELINE config 1), '
-                         'torch CPU fp32 oracle port' % bs}
+        t, bs, kind, impl, threads = time_cpu_steps(a, steps=8, warmup=1)
+        cpu = {'value': bs / t, 'unit': 'clips/s', 'cores': threads, 'kind': kind,
+               'sample': '8 train steps (fwd+CE+top-k+bwd+Adam) of %d clips each (BASELINE config 1 batch), %s' % (bs, impl)}
 
     if rank == 0:
         line = {'metric': METRIC, 'value': value, 'unit': 'clips/s', 'n_gpus': world, 'steps': a.steps,
                 'warmup': a.warmup, 'ms_per_step': ms_step, 'higher_is_better': True, 'scaling': 'weak',
                 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic', 'config': workload(a, world),
                 'clocks': clocks, 'e2e': e2e, 'gpu_launches': int(launches), 'roofline': roof,
-                'cpu_baseline': cpu, 'kernel_families_ms': fam, 'loss': last_loss}
+                'cpu_baseline': cpu, 'kernel_families_ms': fam, 'loss': last_loss,
+                'allreduce_ms': allreduce_ms, 'rank_ms_per_step': rank_ms,
+                'stock_cuda': stock,
+                'vs_stock_cuda': (value / stock['clips_s']) if stock and stock.get('clips_s') else None}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

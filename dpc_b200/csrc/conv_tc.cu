@@ -1650,7 +1650,9 @@ extern "C" int dpc_conv3d_wgrad_tc(const dpc_conv_geom* g, const void* x_hi, con
     p.ktiles_per_split = (total_tiles + splits - 1) / splits;
     // bound the in-TMEM accumulation chain (truncating adds): <= 512 position tiles (2048 UMMA steps,
     // ~ -4e-5 relative); longer reductions continue through the fp32 (round-to-nearest) atomics
-    if (p.ktiles_per_split > 512) p.ktiles_per_split = 512;   // (more, shorter CTAs measured slower: prologue + atomics)
+    int max_kt = 512;                                         // (more, shorter CTAs measured slower: prologue + atomics)
+    if (const char* e = getenv("DPC_WGRAD_MAX_KTILES")) if (atoi(e) > 0) max_kt = atoi(e);     // test knob: force the cap
+    if (p.ktiles_per_split > max_kt) p.ktiles_per_split = max_kt;
     splits = (total_tiles + p.ktiles_per_split - 1) / p.ktiles_per_split;
     DPC_REQUIRE(splits <= 65535, "dpc_conv3d_wgrad_tc: too many K splits (%d)", splits);
     p.splits = splits;

@@ -42,13 +42,22 @@ class FlatTrainer:
         self.step_count = 0
         self.group = process_group
         self.world = dist.get_world_size(process_group) if dist.is_available() and dist.is_initialized() else 1
+        if self.world > 1:
+            # replicas start identical whatever each rank's RNG did (nn.DataParallel re-broadcasts rank 0's parameters
+            # every forward, main.py:65; one process per GPU needs it once)
+            src = dist.get_global_rank(process_group, 0) if process_group is not None else 0
+            dist.broadcast(self.flat_p, src=src, group=process_group)
 
     def zero_grad(self):
         self.flat_g.zero_()
 
     def allreduce(self):
         if self.world > 1:
+            from . import engine
+            tok = engine._TIMER.start('allreduce') if engine._TIMER is not None else None
             dist.all_reduce(self.flat_g, op=dist.ReduceOp.SUM, group=self.group)
+            if tok is not None:
+                engine._TIMER.stop(tok)
 
     def step(self):
         """all-reduce (sum) + Adam with the 1/world average folded into the update"""

@@ -1,0 +1,318 @@
+"""GPU: parity AT THE BENCHMARKED SIZES (BASELINE configs 2 and 4), i.e. the code paths the small fixtures never reach:
+
+  * halo-patch conv / dgrad / wgrad with hundreds of tiles per CTA and the multi-chain TMEM drain of wgrad_halo_kernel
+    (conv_tc.cu: `hp.chain = 64`: > 64 tiles per CTA needs NB > 210 at 32x32x5);
+  * the wgrad split cap (`ktiles_per_split > 512` -> continuation through the fp32 atomics), forced both by size and by
+    the DPC_WGRAD_MAX_KTILES knob;
+  * the persistent conv kernel walking >= 100 tiles per CTA;
+  * BatchNorm statistics / apply / backward over 2.1e7 rows (fp64 atomics at config-2 scale);
+  * the whole train step at config 2 EXACTLY (R18, 128^2, B = 128) and at config 4's per-GPU shard (R34, 224^2, B = 11)
+    against the oracle run on the same GPU in fp32 (TF32 off) -- the same functional restatement the CPU tests pin to the
+    live reference, on a different device.
+
+Kernel references: cuDNN fp32 (TF32 off) per chunk of blocks, reductions accumulated in fp64; tolerance 5e-5 as in
+test_tc_gpu.py.  /root/reference/backbone/resnet_2d3d.py:13-31,47-116; /root/reference/dpc/model_3d.py:46-98."""
+import io
+import contextlib
+import json
+import math
+import os
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from dpc_b200._lib import ConvGeom
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-3
+
+
+@pytest.fixture(scope='module', autouse=True)
+def _fp32_reference_math():
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    yield
+    torch.cuda.empty_cache()
+
+
+def _lib():
+    from dpc_b200._lib import lib
+    return lib()
+
+
+def _st():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def split(x):
+    hi = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
+    lo = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
+    _lib().split_bf16(x.data_ptr(), hi.data_ptr(), lo.data_ptr(), x.numel(), _st())
+    return hi, lo
+
+
+def _ext(i, k, s, p):
+    return (i + 2 * p - k) // s + 1
+
+
+def _conv_case(NB, T, H, W, Ci, Co, k, s, p, chunk, seed=11):
+    """fwd (+ fused BN statistics), dgrad, wgrad of one conv site at full size; reference = cuDNN fp32 per chunk of
+    `chunk` blocks (rows are channels-last: [NB, T, H, W, C]), wgrad / statistics accumulated in fp64"""
+    L = _lib()
+    taps = k[0] * k[1] * k[2]
+    To, Ho, Wo = _ext(T, k[0], s[0], p[0]), _ext(H, k[1], s[1], p[1]), _ext(W, k[2], s[2], p[2])
+    g = torch.Generator(device='cuda').manual_seed(seed)
+    x = torch.randn(NB, T, H, W, Ci, device='cuda', generator=g)                       # channels-last rows
+    dy = torch.randn(NB, To, Ho, Wo, Co, device='cuda', generator=g)
+    w = torch.randn(Co, Ci, *k, device='cuda', generator=g) / math.sqrt(Ci * taps)
+    bf = dict(dtype=torch.bfloat16, device='cuda')
+    wfh, wfl = torch.empty(Co, taps, Ci, **bf), torch.empty(Co, taps, Ci, **bf)
+    wdh, wdl = torch.empty(Ci, taps, Co, **bf), torch.empty(Ci, taps, Co, **bf)
+    L.pack_conv_weight_bf16(w.data_ptr(), wfh.data_ptr(), wfl.data_ptr(), wdh.data_ptr(), wdl.data_ptr(), Co, Ci, taps, _st())
+    xh, xl = split(x)
+    dh, dl = split(dy)
+    geom = ConvGeom(NB, T, H, W, Ci, To, Ho, Wo, Co, k[0], k[1], k[2], s[0], s[1], s[2], p[0], p[1], p[2])
+    y = torch.full((NB, To, Ho, Wo, Co), float('nan'), device='cuda')
+    ws = torch.empty(2 * Co, dtype=torch.float64, device='cuda')
+    L.conv3d_fwd_tc(geom, xh.data_ptr(), xl.data_ptr(), wfh.data_ptr(), wfl.data_ptr(), y.data_ptr(), ws.data_ptr(), _st())
+    dx = torch.full((NB, T, H, W, Ci), float('nan'), device='cuda')
+    L.conv3d_dgrad_tc(geom, dh.data_ptr(), dl.data_ptr(), wdh.data_ptr(), wdl.data_ptr(), dx.data_ptr(), 0, _st())
+    dwp = torch.empty(Co, taps, Ci, device='cuda')
+    dw = torch.full_like(w, float('nan'))
+    L.conv3d_wgrad_tc(geom, xh.data_ptr(), xl.data_ptr(), dh.data_ptr(), dl.data_ptr(), dwp.data_ptr(), dw.data_ptr(), _st())
+    torch.cuda.synchronize()
+    del xh, xl, dh, dl
+    assert not torch.isnan(y).any() and not torch.isnan(dx).any() and not torch.isnan(dw).any()
+    dw_ref = torch.zeros(w.shape, dtype=torch.float64, device='cuda')
+    s1 = torch.zeros(Co, dtype=torch.float64, device='cuda')
+    s2 = torch.zeros(Co, dtype=torch.float64, device='cuda')
+    ey = edx = 0.0
+    my = mdx = 0.0
+    for n0 in range(0, NB, chunk):
+        xc = x[n0:n0 + chunk].permute(0, 4, 1, 2, 3).contiguous().requires_grad_(True)
+        wc = w.clone().requires_grad_(True)
+        yc = F.conv3d(xc, wc, None, s, p)
+        yc.backward(dy[n0:n0 + chunk].permute(0, 4, 1, 2, 3))
+        yr = yc.detach().permute(0, 2, 3, 4, 1)
+        ey = max(ey, float((y[n0:n0 + chunk] - yr).abs().max()))
+        my = max(my, float(yr.abs().max()))
+        dr = xc.grad.permute(0, 2, 3, 4, 1)
+        edx = max(edx, float((dx[n0:n0 + chunk] - dr).abs().max()))
+        mdx = max(mdx, float(dr.abs().max()))
+        dw_ref += wc.grad.double()
+        yd = yr.double().reshape(-1, Co)
+        s1 += yd.sum(0)
+        s2 += (yd * yd).sum(0)
+        del xc, yc, yr, dr, yd
+    rows = NB * To * Ho * Wo
+    assert ey / my < 5e-5, ('fwd', ey / my)
+    assert edx / mdx < 5e-5, ('dgrad', edx / mdx)
+    ew = float((dw.double() - dw_ref).abs().max() / dw_ref.abs().max())
+    assert ew < 5e-5, ('wgrad', ew)
+    mean, rstd = torch.empty(Co, device='cuda'), torch.empty(Co, device='cuda')
+    L.bn_finalize(ws.data_ptr(), rows, Co, 1e-5, mean.data_ptr(), rstd.data_ptr(), _st())
+    m_ref = s1 / rows
+    v_ref = s2 / rows - m_ref * m_ref
+    assert float((mean.double() - m_ref).abs().max()) < 1e-5 * my
+    assert float(((rstd.double() - 1 / torch.sqrt(v_ref + 1e-5)).abs() * torch.sqrt(v_ref + 1e-5)).max()) < 1e-5
+    return ey / my, edx / mdx, ew
+
+
+def test_halo_kernels_hundreds_of_tiles_per_cta():
+    """layer1 site (64 -> 64, 1x3x3, 32x32x5) at NB = 256: 11 520 tiles = 78 per CTA -> conv_tc_halo_kernel's ring phases
+    over many tiles, and wgrad_halo_kernel's SECOND accumulation chain (chain = 64 tiles) with the atomics drain"""
+    print(_conv_case(256, 5, 32, 32, 64, 64, (1, 3, 3), (1, 1, 1), (0, 1, 1), chunk=32))
+
+
+def test_halo_kernels_config2_extent():
+    """the same site at config 2's full extent (NB = 1024: 311 tiles per CTA, 5 chains)"""
+    print(_conv_case(1024, 5, 32, 32, 64, 64, (1, 3, 3), (1, 1, 1), (0, 1, 1), chunk=64))
+
+
+def test_persistent_conv_100_tiles_per_cta():
+    """layer2 site (128 -> 128, 1x3x3, 16x16x5) at NB = 1536: 15 360 tiles = 104 per CTA on conv_tc_persist_kernel
+    (config 2 itself: 69 per CTA)"""
+    print(_conv_case(1536, 5, 16, 16, 128, 128, (1, 3, 3), (1, 1, 1), (0, 1, 1), chunk=128))
+
+
+def test_layer3_site_config2_extent():
+    """the dominant kernel of the bench line: 256 -> 256, 3x3x3, 8x8x3 at NB = 1024 (196 608 rows)"""
+    print(_conv_case(1024, 3, 8, 8, 256, 256, (3, 3, 3), (1, 1, 1), (1, 1, 1), chunk=256))
+
+
+def test_wgrad_split_cap_by_size():
+    """256 -> 256, 3x3x3 at 8x8x3 with NB = 2048: 6144 position tiles over the wave-chosen 8 splits = 768 per split
+    > the 512-tile cap on one in-TMEM chain -> the cap re-splits and the partial sums meet in the fp32 atomics"""
+    print(_conv_case(2048, 3, 8, 8, 256, 256, (3, 3, 3), (1, 1, 1), (1, 1, 1), chunk=512))
+
+
+def test_wgrad_split_cap_forced_small():
+    """the same branch forced at a small size: chains of <= 4 position tiles"""
+    os.environ['DPC_WGRAD_MAX_KTILES'] = '4'
+    try:
+        print(_conv_case(24, 3, 8, 8, 256, 256, (3, 3, 3), (1, 1, 1), (1, 1, 1), chunk=24))
+        print(_conv_case(6, 5, 16, 16, 128, 128, (1, 3, 3), (1, 1, 1), (0, 1, 1), chunk=6))
+    finally:
+        del os.environ['DPC_WGRAD_MAX_KTILES']
+
+
+def test_batchnorm_2e7_rows():
+    """bn1 of config 2: 1024 x 5 x 64 x 64 = 20 971 520 rows x 64 channels (5.4 GB): statistics, apply (+ operand
+    planes), backward (reduce + apply) against fp64 sums accumulated over chunks"""
+    from dpc_b200 import engine as E
+    rows, C = 1024 * 5 * 64 * 64, 64
+    st = _st()
+    g = torch.Generator(device='cuda').manual_seed(21)
+    y = torch.randn(rows, C, device='cuda', generator=g)
+    y.mul_(torch.rand(C, device='cuda', generator=g) * 2 + 0.5).add_(torch.randn(C, device='cuda', generator=g))
+    gamma = torch.rand(C, device='cuda', generator=g) + 0.5
+    beta = torch.randn(C, device='cuda', generator=g) * 0.1
+    mean, rstd = E._bn_stats(y, rows, C, st)
+    CH = 1 << 20
+    s1 = torch.zeros(C, dtype=torch.float64, device='cuda')
+    s2 = torch.zeros_like(s1)
+    for r0 in range(0, rows, CH):
+        yd = y[r0:r0 + CH].double()
+        s1 += yd.sum(0)
+        s2 += (yd * yd).sum(0)
+    m64 = s1 / rows
+    v64 = s2 / rows - m64 * m64
+    r64 = 1 / torch.sqrt(v64 + 1e-5)
+    assert float((mean.double() - m64).abs().max()) < 1e-6 * float(y.abs().max())
+    assert float(((rstd.double() - r64) / r64).abs().max()) < 1e-6
+    out, pl = E._bn_apply(y, mean, rstd, gamma, beta, True, rows, C, st, want_rows=True, want_planes=True)
+    dout = torch.randn(rows, C, device='cuda', generator=g)
+    dy, _, dg, db, _ = E._bn_bwd(dout, out, True, y, mean, rstd, gamma, rows, C, st)
+    torch.cuda.synchronize()
+    sg = torch.zeros(C, dtype=torch.float64, device='cuda')
+    sgx = torch.zeros_like(sg)
+    eo = 0.0
+    for r0 in range(0, rows, CH):
+        yd = y[r0:r0 + CH].double()
+        xhat = (yd - m64) * r64
+        o = torch.relu(xhat * gamma.double() + beta.double())
+        eo = max(eo, float((out[r0:r0 + CH].double() - o).abs().max()))
+        gg = dout[r0:r0 + CH].double() * (out[r0:r0 + CH] > 0).double()
+        sg += gg.sum(0)
+        sgx += (gg * xhat).sum(0)
+    assert eo < 1e-5 * float(out.abs().max())
+    assert float(((pl[0].float() + pl[1].float())[:CH] - out[:CH]).abs().max()) < 2e-5 * float(out.abs().max())
+    assert float(((db.double() - sg) / sg.abs().clamp_min(1.0)).abs().max()) < 5e-5
+    assert float(((dg.double() - sgx) / sgx.abs().clamp_min(1.0)).abs().max()) < 5e-5
+    ed = md = 0.0
+    for r0 in list(range(0, rows, CH))[::4]:
+        yd = y[r0:r0 + CH].double()
+        xhat = (yd - m64) * r64
+        gg = dout[r0:r0 + CH].double() * (out[r0:r0 + CH] > 0).double()
+        d = gamma.double() * r64 * (gg - sg / rows - xhat * sgx / rows)
+        ed = max(ed, float((dy[r0:r0 + CH].double() - d).abs().max()))
+        md = max(md, float(d.abs().max()))
+    assert ed / md < 5e-5, ed / md
+
+
+# =====================================================================================================================
+# whole train step at the benchmarked configurations
+# =====================================================================================================================
+def _build(network, img, pred_step, sd):
+    import dpc_b200
+    with contextlib.redirect_stdout(io.StringIO()):
+        m = dpc_b200.DPC_RNN(sample_size=img, num_seq=8, seq_len=5, network=network, pred_step=pred_step)
+    m.load_state_dict(sd, strict=True)
+    return m.cuda()
+
+
+def _rel(a, b):
+    a, b = a.detach().double().reshape(-1), b.detach().double().reshape(-1)
+    return float((a - b).abs().max() / b.abs().max().clamp_min(1e-30)), float((a - b).norm() / b.norm().clamp_min(1e-30))
+
+
+def _step_vs_oracle(network, img, B, seed):
+    """one eval-mode step (dropout off; BN still batch statistics, SURVEY 3.4 trap 1) of the product path vs the oracle on
+    the same GPU; returns the measured errors"""
+    from oracle import dpc_oracle as O
+    import dpc_b200
+    sd = O.synthetic_state_dict(network, seed)
+    m = _build(network, img, 3, sd).eval()
+    g = torch.Generator().manual_seed(seed + 1)
+    block = torch.randn(B, 8, 3, 5, img, img, generator=g).cuda()
+    score, mask = m(block)
+    feat_fn = m.backbone
+    loss = dpc_b200.NCECriterion()(score)
+    loss.backward()
+    torch.cuda.synchronize()
+    ours = dict(score=score.detach().clone(), loss=float(loss), mask=mask,
+                grads={k: p.grad.detach().clone() for k, p in m.named_parameters()})
+    with torch.no_grad():
+        ours['feat'] = feat_fn(block.view(-1, 3, 5, img, img)).clone()
+    del m, score, loss
+    torch.cuda.empty_cache()
+    sdc = {k: v.cuda() for k, v in sd.items()}
+    taps = {}
+    with torch.no_grad():
+        ref_feat = O.backbone_forward(block.view(-1, 3, 5, img, img), sdc, network)
+    res = {'B': B, 'network': network, 'img': img}
+    res['feat_max'], res['feat_l2'] = _rel(ours['feat'], ref_feat)
+    del ref_feat
+    ref_loss, ref_score, ref_grads = O.train_step_grads(block, sdc, network, 3)
+    res['score_max'], res['score_l2'] = _rel(ours['score'], ref_score)
+    res['loss'], res['ref_loss'] = ours['loss'], float(ref_loss)
+    L = int(math.ceil(img / 32))
+    assert torch.equal(ours['mask'].cpu(), O.closed_form_mask(B, 3, L))
+    num = den = 0.0
+    worst, worst_k = 0.0, None
+    for k, gk in ours['grads'].items():
+        d = (gk - ref_grads[k]).double()
+        r = float(d.norm() / ref_grads[k].double().norm().clamp_min(1e-30))
+        if r > worst:
+            worst, worst_k = r, k
+        num += float(d.pow(2).sum())
+        den += float(ref_grads[k].double().pow(2).sum())
+    res['grad_all_l2'] = (num / den) ** 0.5
+    res['grad_worst_l2'], res['grad_worst_name'] = worst, worst_k
+    return res
+
+
+def _record(res):
+    """measured errors -> gpurun_out/parity_at_scale.jsonl (copied to profiles/ when committed)"""
+    d = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'gpurun_out')
+    os.makedirs(d, exist_ok=True)
+    with open(os.path.join(d, 'parity_at_scale.jsonl'), 'a') as f:
+        f.write(json.dumps(res) + '\n')
+    print(json.dumps(res))
+
+
+# end-to-end gradient rel-L2 against the fp32 oracle as the batch grows (profiles/r2_grad_table.md): the tiny-batch chaos
+# (ReLU flips / BatchNorm cancellation, test_parity_gpu.GRAD_TOL) averages out; at the benchmarked size the whole gradient
+# vector must be within 5e-3 and every tensor within 1e-2
+GRAD_TOL_ALL_B128, GRAD_TOL_WORST_B128 = 5e-3, 1e-2
+
+
+def test_config2_exact_train_step_vs_oracle_on_device():
+    """BASELINE config 2 exactly: 2d3d-R18, 128^2, B = 128 (NB = 1024, M = 6144)"""
+    res = _step_vs_oracle('resnet18', 128, 128, 51)
+    _record(res)
+    assert res['feat_max'] < TOL and res['feat_l2'] < TOL, res
+    assert res['score_max'] < TOL and res['score_l2'] < TOL, res
+    assert abs(res['loss'] - res['ref_loss']) < TOL * max(1.0, abs(res['ref_loss'])), res
+    assert res['grad_all_l2'] < GRAD_TOL_ALL_B128 and res['grad_worst_l2'] < GRAD_TOL_WORST_B128, res
+
+
+def test_config4_shard_train_step_vs_oracle_on_device():
+    """BASELINE config 4's per-GPU shard: 2d3d-R34, 224^2, B = 11 (global 44 on 4 GPUs, README.md:49; M = 1617)"""
+    res = _step_vs_oracle('resnet34', 224, 11, 61)
+    _record(res)
+    assert res['feat_max'] < TOL and res['feat_l2'] < TOL, res
+    assert res['score_max'] < TOL and res['score_l2'] < TOL, res
+    assert abs(res['loss'] - res['ref_loss']) < TOL * max(1.0, abs(res['ref_loss'])), res
+    assert res['grad_all_l2'] < 2e-2 and res['grad_worst_l2'] < 4e-2, res
+
+
+@pytest.mark.parametrize('B', [2, 8, 32])
+def test_gradient_error_falls_with_batch(B):
+    """the rows of profiles/r2_grad_table.md below the benchmarked size (R18, 128^2)"""
+    res = _step_vs_oracle('resnet18', 128, B, 70 + B)
+    _record(res)
+    assert res['score_max'] < TOL and res['score_l2'] < TOL, res
+    assert res['grad_all_l2'] < 2e-2, res

@@ -102,6 +102,24 @@ CASES = [
     (9, 5, 30, 30, 64, 64, (1, 3, 3), (1, 1, 1), (0, 1, 1)),
     # 64 -> 64 frames too wide for the halo-patch kernels' shared-memory budget: tap-per-box fallback
     (1, 2, 56, 56, 64, 64, (1, 3, 3), (1, 1, 1), (0, 1, 1)),
+    # Bottleneck2d / 3d sites (resnet_2d3d.py:119-202; every Ci / Co / stride combination of backbone_spec('resnet50')):
+    # 1x1x1 reductions / expansions up to 1024 channels (grid.y > 1 with BN = 256, wgrad with Ci = 1024), strided
+    # 1x1x1 downsamples, the strided 3x3 after a 1x1x1
+    (3, 5, 16, 16, 64, 64, (1, 1, 1), (1, 1, 1), (0, 0, 0)),        # layer1.0.conv1
+    (3, 5, 16, 16, 64, 256, (1, 1, 1), (1, 1, 1), (0, 0, 0)),       # layer1.x.conv3 / layer1.0.downsample
+    (3, 5, 16, 16, 256, 64, (1, 1, 1), (1, 1, 1), (0, 0, 0)),       # layer1.1.conv1
+    (3, 5, 16, 16, 256, 128, (1, 1, 1), (1, 1, 1), (0, 0, 0)),      # layer2.0.conv1
+    (3, 5, 16, 16, 128, 128, (1, 3, 3), (1, 2, 2), (0, 1, 1)),      # layer2.0.conv2 (carries the stride)
+    (3, 5, 8, 8, 128, 512, (1, 1, 1), (1, 1, 1), (0, 0, 0)),        # layer2.x.conv3
+    (3, 5, 16, 16, 256, 512, (1, 1, 1), (1, 2, 2), (0, 0, 0)),      # layer2.0.downsample
+    (3, 5, 8, 8, 512, 128, (1, 1, 1), (1, 1, 1), (0, 0, 0)),        # layer2.1.conv1
+    (3, 5, 8, 8, 512, 256, (1, 1, 1), (1, 1, 1), (0, 0, 0)),        # layer3.0.conv1
+    (3, 5, 8, 8, 256, 256, (3, 3, 3), (2, 2, 2), (1, 1, 1)),        # layer3.0.conv2
+    (3, 3, 4, 4, 256, 1024, (1, 1, 1), (1, 1, 1), (0, 0, 0)),       # layer3.x.conv3
+    (3, 5, 8, 8, 512, 1024, (1, 1, 1), (2, 2, 2), (0, 0, 0)),       # layer3.0.downsample
+    (3, 3, 4, 4, 1024, 256, (1, 1, 1), (1, 1, 1), (0, 0, 0)),       # layer3.1.conv1 / layer4.0.conv1
+    (3, 3, 4, 4, 1024, 1024, (1, 1, 1), (2, 2, 2), (0, 0, 0)),      # layer4.0.downsample
+    (3, 2, 2, 2, 256, 1024, (1, 1, 1), (1, 1, 1), (0, 0, 0)),       # layer4.x.conv3 (2x2x2 map: < one tile)
 ]
 
 
