@@ -42,6 +42,13 @@ _SIGS = {
     'dpc_stem_s2d_pack': (c_int, [P, P, P, c_int, c_int, c_int, c_int, P]),
     'dpc_stem_conv_fwd_s2d': (c_int, [P, P, P, P, P, P, c_int, c_int, c_int, c_int, P]),
     'dpc_stem_conv_wgrad_s2d': (c_int, [P, P, P, P, P, c_int, c_int, c_int, c_int, P]),
+    'dpc_stem_pool_supported': (c_int, [c_int, c_int]),
+    'dpc_stem_s2d_wpack': (c_int, [P, P, P]),
+    'dpc_stem_pool_fwd': (c_int, [P, P, P, P, P, P, P, c_int, c_int, c_int, c_int, P]),
+    'dpc_stem_pool_finalize': (c_int, [P, P, P, P, P, P, P, P, P, c_int64, P]),
+    'dpc_stem_pool_bwd_reduce': (c_int, [P, P, P, P, P, P, P, P, c_int64, P]),
+    'dpc_stem_pool_bwd': (c_int, [P, P, P, P, P, P, P, P, P, P, P, c_int, c_int, c_int, c_int, P]),
+    'dpc_stem_pool_bwd_wgrad': (c_int, [P, P, P, P, P, P, P, P, P, P, c_int, c_int, c_int, c_int, P]),
     'dpc_bn_stats': (c_int, [P, c_int64, c_int, P, P, P, c_float, P]),
     'dpc_bn_finalize': (c_int, [P, c_int64, c_int, c_float, P, P, P]),
     'dpc_bn_apply_fwd': (c_int, [P, P, P, P, P, P, P, P, P, P, P, P, c_int, P, P, P, c_int64, c_int, P]),
@@ -95,7 +102,7 @@ class _Lib:
                 raise DpcLibError('libdpc_b200.so does not export %s (stale build?)' % name)
             fn.restype = res
             fn.argtypes = args
-            if res is c_int and name != 'dpc_abi_version':
+            if res is c_int and name not in ('dpc_abi_version', 'dpc_stem_pool_supported'):
                 setattr(self, name[4:], self._checked(fn, name))
             else:
                 setattr(self, name[4:], fn)

@@ -422,6 +422,15 @@ extern "C" int dpc_stem_s2d_pack(const float* x, void* x2_hi, void* x2_lo, int N
     return DPC_OK;
 }
 
+// w [64,3,1,7,7] fp32 -> the packed split-bf16 filter bank `wp` (32768 bf16: 16 taps x [W_hi ; W_lo] x 64 x 16) that the
+// pooled-stem kernels (stem_pool.cu) keep resident in shared memory
+extern "C" int dpc_stem_s2d_wpack(const float* w, void* wp, void* stream) {
+    DPC_REQUIRE(w && wp, "dpc_stem_s2d_wpack: bad args");
+    stem_s2d_wpack_kernel<<<(S2D_TAPS * S2D_BN * S2D_CH + 255) / 256, 256, 0, as_stream(stream)>>>(w, reinterpret_cast<__nv_bfloat16*>(wp));
+    DPC_LAUNCH_CHECK();
+    return DPC_OK;
+}
+
 // y [NB,T,H/2,W/2,64] = conv1(x) from the space-to-depth planes; `wp`: scratch of 32768 bf16 for the packed filter
 // bank; bn_ws (nullable): 128 doubles = per-channel sum | sum of squares of y
 extern "C" int dpc_stem_conv_fwd_s2d(const void* x2_hi, const void* x2_lo, const float* w, void* wp, float* y, double* bn_ws,

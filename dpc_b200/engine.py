@@ -158,6 +158,10 @@ USE_TC = True
 # than the separate coalesced reduce pass they replace (layer1 dgrad 1.06 -> 2.34 ms vs a 0.52 ms reduce; layer2
 # +0.38 vs 0.26; layer3 +0.31 vs 0.10).  Needs a smem-staged, column-contiguous epilogue to pay off.
 FUSE_BN_REDUCE = False
+# conv1 + bn1 + relu + maxpool without storing the conv1 output (stem_pool.cu); False = round-1 stem kernels
+STEM_POOL = True
+# ... and conv1's wgrad inside the recomputing backward kernel (the gradient on the conv1 grid is never stored either)
+STEM_FUSE_WGRAD = True
 
 
 @_timed('split_bf16')
@@ -323,18 +327,10 @@ def _conv_bn(site, op, name, bn_state, training, st):
     return y, m, r
 
 
-def backbone_forward(network, x, P, need_ctx=True, bn_state=None, training=True):
-    """x [NB,3,T,H,W] fp32 contiguous CUDA; P: name -> tensor.  Returns (feature rows [NB*To*Ho*Wo, 256],
-    (To,Ho,Wo), ctx).  bn_state: None (track_running_stats=False: batch statistics always) or
-    {bn name: (running_mean, running_var)} (track_running_stats=True, eval/model_3d_lc.py:26)."""
-    L = lib()
-    st = _stream()
-    running = bn_state is not None and not training
-    if running and need_ctx:
-        raise NotImplementedError('backward through eval-mode (running-statistics) BatchNorm is not built')
+def _stem_forward_unpooled(L, st, x, P, bn_state, training, running, network):
+    """conv1 -> y0 (stored) -> bn1 + relu + maxpool: the exact-fp32 CUDA-core path (USE_TC = False), odd frame sizes
+    (stem_tc.cu) and frames the pooled-stem schedule does not cover.  Returns (a0 rows, conv operand, ctx)."""
     NB, Cin, T, H, W = x.shape
-    if Cin != 3:
-        raise ValueError('backbone expects 3 input channels, got %d' % Cin)
     Ho, Wo = _out_extent(H, 7, 2, 3), _out_extent(W, 7, 2, 3)
     rows0 = NB * T * Ho * Wo
     y0 = _empty((rows0, 64), x)
@@ -371,11 +367,61 @@ def backbone_forward(network, x, P, need_ctx=True, bn_state=None, training=True)
     _timed('stem_pool_fwd')(L.bn_relu_maxpool_fwd)(ptr(y0), ptr(m0), ptr(r0), ptr(P['bn1.weight']), ptr(P['bn1.bias']), ptr(a0),
                           NB * T, Ho, Wo, 64, st)
     ctx = dict(network=network, x=x, x2=x2, y0=y0, m0=m0, r0=r0, a0=a0, stem_dims=(NB, T, H, W, Ho, Wo), blocks=[])
-    cur, dims, C = a0, (T, Hp, Wp), 64
+    cur = a0
+    cur_op = _split(cur, st) if USE_TC else cur
+    return cur, cur_op, ctx
+
+
+def backbone_forward(network, x, P, need_ctx=True, bn_state=None, training=True):
+    """x [NB,3,T,H,W] fp32 contiguous CUDA; P: name -> tensor.  Returns (feature rows [NB*To*Ho*Wo, 256],
+    (To,Ho,Wo), ctx).  bn_state: None (track_running_stats=False: batch statistics always) or
+    {bn name: (running_mean, running_var)} (track_running_stats=True, eval/model_3d_lc.py:26)."""
+    L = lib()
+    st = _stream()
+    running = bn_state is not None and not training
+    if running and need_ctx:
+        raise NotImplementedError('backward through eval-mode (running-statistics) BatchNorm is not built')
+    NB, Cin, T, H, W = x.shape
+    if Cin != 3:
+        raise ValueError('backbone expects 3 input channels, got %d' % Cin)
+    Ho, Wo = _out_extent(H, 7, 2, 3), _out_extent(W, 7, 2, 3)
+    rows0 = NB * T * Ho * Wo
+    x2 = None
+    Hp, Wp = _out_extent(Ho, 3, 2, 1), _out_extent(Wo, 3, 2, 1)
+    rows_p = NB * T * Hp * Wp
+    bf = dict(dtype=torch.bfloat16, device=x.device)
+    pooled = USE_TC and STEM_POOL and L.stem_pool_supported(H, W) >= 1
+    if pooled:
+        # conv1 + bn1 + relu + maxpool with the conv1 output never stored (stem_pool.cu): the kernel keeps, per pooled
+        # position, the conv value the pool selects (+ its window index) and bn1's batch sums over all conv positions
+        x2 = (torch.empty((NB, T, H // 2, W // 2, 16), **bf), torch.empty((NB, T, H // 2, W // 2, 16), **bf))
+        wp = torch.empty(32768, **bf)
+        ypool = _empty((rows_p, 64), x)
+        idx = torch.empty((rows_p, 64), dtype=torch.uint8, device=x.device)
+        ws0 = None if running else torch.empty(128, dtype=torch.float64, device=x.device)
+        _timed('stem_fwd')(L.stem_s2d_pack)(ptr(x), ptr(x2[0]), ptr(x2[1]), NB, T, H, W, st)
+        L.stem_s2d_wpack(ptr(P['conv1.weight']), ptr(wp), st)
+        _timed('stem_fwd')(L.stem_pool_fwd)(ptr(x2[0]), ptr(x2[1]), ptr(wp), ptr(P['bn1.weight']), ptr(ypool), ptr(idx), ptr(ws0),
+                                            NB, T, H, W, st)
+        if running:
+            m0 = bn_state['bn1'][0]
+            r0 = torch.empty_like(m0)
+            L.bn_rstd_from_var(ptr(bn_state['bn1'][1]), BN_EPS, ptr(r0), 64, st)
+        else:
+            m0, r0 = _empty((64,), x), _empty((64,), x)
+            L.bn_finalize(ptr(ws0), rows0, 64, BN_EPS, ptr(m0), ptr(r0), st)
+            if bn_state is not None:
+                L.bn_running_update(ptr(m0), ptr(r0), rows0, BN_EPS, BN_MOMENTUM, ptr(bn_state['bn1'][0]), ptr(bn_state['bn1'][1]), 64, st)
+        a0p = (torch.empty((rows_p, 64), **bf), torch.empty((rows_p, 64), **bf))
+        _timed('stem_pool_fwd')(L.stem_pool_finalize)(ptr(ypool), ptr(idx), ptr(m0), ptr(r0), ptr(P['bn1.weight']), ptr(P['bn1.bias']),
+                                                      ptr(a0p[0]), ptr(a0p[1]), None, rows_p, st)
+        ctx = dict(network=network, x=x, x2=x2, wp=wp, ypool=ypool, idx=idx, m0=m0, r0=r0, stem_dims=(NB, T, H, W, Ho, Wo), blocks=[])
+        cur, cur_op = None, a0p
+    else:
+        cur, cur_op, ctx = _stem_forward_unpooled(L, st, x, P, bn_state, training, running, network)
+    dims, C = (T, Hp, Wp), 64
     tc = USE_TC
     Site = TcConvSite if tc else ConvSite
-    # conv operands: split-bf16 planes on the tensor-core path, fp32 rows on the CUDA-core path
-    cur_op = _split(cur, st) if tc else cur
     spec = backbone_spec(network)
     for bi, b in enumerate(spec):
         p = b['name']
@@ -513,6 +559,34 @@ def backbone_backward(ctx, dout, P):
     return G
 
 
+def _stem_backward_unpooled(L, st, ctx, dout, P, G):
+    """backward of _stem_forward_unpooled; fills G['bn1.*'] and returns dW of conv1"""
+    NB, T, H, W, Ho, Wo = ctx['stem_dims']
+    rows0 = NB * T * Ho * Wo
+    # max-pool bwd + ReLU bwd + bn1 bwd fused: the 5.4 GB (B=128) gradient on the conv1 grid is never stored
+    tc = USE_TC
+    y0 = ctx['y0']
+    dy0 = None if tc else torch.empty_like(y0)
+    dy0p = (torch.empty(y0.shape, dtype=torch.bfloat16, device=y0.device),
+            torch.empty(y0.shape, dtype=torch.bfloat16, device=y0.device)) if tc else (None, None)
+    ws = torch.empty(128, dtype=torch.float64, device=y0.device)
+    G['bn1.weight'], G['bn1.bias'] = _empty((64,), y0), _empty((64,), y0)
+    _timed('stem_tail_bwd')(L.stem_tail_bwd)(ptr(y0), ptr(ctx['m0']), ptr(ctx['r0']), ptr(P['bn1.weight']),
+                                             ptr(P['bn1.bias']), ptr(ctx['a0']), ptr(dout), ptr(ws),
+                                             ptr(G['bn1.weight']), ptr(G['bn1.bias']), ptr(dy0), ptr(dy0p[0]),
+                                             ptr(dy0p[1]), NB * T, Ho, Wo, 64, 1, st)
+    del dout
+    dw0 = torch.empty_like(P['conv1.weight'])
+    if tc and ctx.get('x2') is not None:
+        x2 = ctx['x2']
+        _timed('stem_wgrad')(L.stem_conv_wgrad_s2d)(ptr(x2[0]), ptr(x2[1]), ptr(dy0p[0]), ptr(dy0p[1]), ptr(dw0), NB, T, H, W, st)
+    elif tc:
+        _timed('stem_wgrad')(L.stem_conv_wgrad_tc)(ptr(ctx['x']), ptr(dy0p[0]), ptr(dy0p[1]), ptr(dw0), NB, T, H, W, st)
+    else:
+        _timed('stem_wgrad')(L.stem_conv_wgrad)(ptr(ctx['x']), ptr(dy0), ptr(dw0), NB, T, H, W, st)
+    return dw0
+
+
 def _backbone_backward(ctx, dout, P, side):
     L = lib()
     st = _stream()
@@ -615,27 +689,33 @@ def _backbone_backward(ctx, dout, P, side):
         rec.clear()
     NB, T, H, W, Ho, Wo = ctx['stem_dims']
     rows0 = NB * T * Ho * Wo
-    # max-pool bwd + ReLU bwd + bn1 bwd fused: the 5.4 GB (B=128) gradient on the conv1 grid is never stored
-    tc = USE_TC
-    y0 = ctx['y0']
-    dy0 = None if tc else torch.empty_like(y0)
-    dy0p = (torch.empty(y0.shape, dtype=torch.bfloat16, device=y0.device),
-            torch.empty(y0.shape, dtype=torch.bfloat16, device=y0.device)) if tc else (None, None)
-    ws = torch.empty(128, dtype=torch.float64, device=y0.device)
-    G['bn1.weight'], G['bn1.bias'] = _empty((64,), y0), _empty((64,), y0)
-    _timed('stem_tail_bwd')(L.stem_tail_bwd)(ptr(y0), ptr(ctx['m0']), ptr(ctx['r0']), ptr(P['bn1.weight']),
-                                             ptr(P['bn1.bias']), ptr(ctx['a0']), ptr(dout), ptr(ws),
-                                             ptr(G['bn1.weight']), ptr(G['bn1.bias']), ptr(dy0), ptr(dy0p[0]),
-                                             ptr(dy0p[1]), NB * T, Ho, Wo, 64, 1, st)
-    del dout
-    dw0 = torch.empty_like(P['conv1.weight'])
-    if tc and ctx.get('x2') is not None:
-        x2 = ctx['x2']
-        _timed('stem_wgrad')(L.stem_conv_wgrad_s2d)(ptr(x2[0]), ptr(x2[1]), ptr(dy0p[0]), ptr(dy0p[1]), ptr(dw0), NB, T, H, W, st)
-    elif tc:
-        _timed('stem_wgrad')(L.stem_conv_wgrad_tc)(ptr(ctx['x']), ptr(dy0p[0]), ptr(dy0p[1]), ptr(dw0), NB, T, H, W, st)
+    if ctx.get('ypool') is not None:
+        # pooled stem (stem_pool.cu): bn1's backward sums on the pooled grid, then conv1 is RECOMPUTED and its epilogue
+        # turns the pooled gradient into the gradient planes of the conv1 grid -- the conv1 output was never stored
+        dev = dout.device
+        x2, ypool = ctx['x2'], ctx['ypool']
+        rows_p = ypool.shape[0]
+        ws = torch.empty(128, dtype=torch.float64, device=dev)
+        G['bn1.weight'], G['bn1.bias'] = _empty((64,), ypool), _empty((64,), ypool)
+        _timed('stem_tail_bwd')(L.stem_pool_bwd_reduce)(ptr(ypool), ptr(dout), ptr(ctx['idx']), ptr(ctx['m0']), ptr(ctx['r0']), ptr(ws),
+                                                        ptr(G['bn1.weight']), ptr(G['bn1.bias']), rows_p, st)
+        dw0 = torch.empty_like(P['conv1.weight'])
+        if STEM_FUSE_WGRAD and L.stem_pool_supported(H, W) == 2:
+            # conv1's wgrad MMAs run in the same kernel on the gradient tile in shared memory: no 5.4 GB gradient planes
+            _timed('stem_bwd_wgrad')(L.stem_pool_bwd_wgrad)(ptr(x2[0]), ptr(x2[1]), ptr(ctx['wp']), ptr(dout), ptr(ctx['idx']),
+                                                            ptr(ctx['m0']), ptr(ctx['r0']), ptr(P['bn1.weight']), ptr(ws), ptr(dw0),
+                                                            NB, T, H, W, st)
+            del dout
+        else:
+            dy0p = (torch.empty((rows0, 64), dtype=torch.bfloat16, device=dev), torch.empty((rows0, 64), dtype=torch.bfloat16, device=dev))
+            _timed('stem_tail_bwd')(L.stem_pool_bwd)(ptr(x2[0]), ptr(x2[1]), ptr(ctx['wp']), ptr(dout), ptr(ctx['idx']), ptr(ctx['m0']),
+                                                     ptr(ctx['r0']), ptr(P['bn1.weight']), ptr(ws), ptr(dy0p[0]), ptr(dy0p[1]),
+                                                     NB, T, H, W, st)
+            del dout
+            _timed('stem_wgrad')(L.stem_conv_wgrad_s2d)(ptr(x2[0]), ptr(x2[1]), ptr(dy0p[0]), ptr(dy0p[1]), ptr(dw0), NB, T, H, W, st)
     else:
-        _timed('stem_wgrad')(L.stem_conv_wgrad)(ptr(ctx['x']), ptr(dy0), ptr(dw0), NB, T, H, W, st)
+        dw0 = _stem_backward_unpooled(L, st, ctx, dout, P, G)
+        del dout
     G['conv1.weight'] = dw0
     if side is not None:
         main.wait_stream(side)

@@ -89,6 +89,10 @@ int dpc_conv3d_wgrad_tc(const dpc_conv_geom* g, const void* x_hi, const void* x_
  * replaces backbone/resnet_2d3d.py:211,260 (self.conv1).  x [NB,3,T,H,W] -> y [NB,T,H/2,W/2,64]. */
 int dpc_stem_conv_fwd(const float* x, const float* w /*[64,3,1,7,7]*/, float* y,
                       int NB, int T, int H, int W, void* stream);
+/* same, with conv1's weight gradient dw [64,3,1,7,7] computed by the same kernel (needs dpc_stem_pool_supported(H, W) == 2) */
+int dpc_stem_pool_bwd_wgrad(const void* x2_hi, const void* x2_lo, const void* wp, const float* dout, const void* idx,
+                            const float* mean, const float* rstd, const float* gamma, const double* ws, float* dw,
+                            int NB, int T, int H, int W, void* stream);
 int dpc_stem_conv_wgrad(const float* x, const float* dy, float* dw /*[64,3,1,7,7]*/,
                         int NB, int T, int H, int W, void* stream);
 /* tcgen05 versions (3xBF16 split; the im2col tile is built in shared memory from the fp32 video).
@@ -108,6 +112,24 @@ int dpc_stem_conv_fwd_s2d(const void* x2_hi, const void* x2_lo, const float* w, 
 /* dw [64,3,1,7,7] from the space-to-depth planes and the split-bf16 planes of dy [NB,T,H/2,W/2,64] */
 int dpc_stem_conv_wgrad_s2d(const void* x2_hi, const void* x2_lo, const void* dy_hi, const void* dy_lo, float* dw,
                             int NB, int T, int H, int W, void* stream);
+
+/* Pooled stem (stem_pool.cu): conv1 + bn1 + relu + maxpool (backbone/resnet_2d3d.py:211-214,260-263) without ever storing
+ * the conv1 output.  Forward: dpc_stem_s2d_pack -> dpc_stem_s2d_wpack -> dpc_stem_pool_fwd (per pooled position the conv1
+ * value max-pool o relu o bn1 selects + its 3x3-window index; bn1 batch sums over all conv positions) -> dpc_bn_finalize ->
+ * dpc_stem_pool_finalize (normalised, ReLU'd operand planes of layer1; ReLU-dead windows flagged in idx).  Backward:
+ * dpc_stem_pool_bwd_reduce (bn1 backward sums on the pooled grid) -> dpc_stem_pool_bwd (conv1 recomputed; gradient planes on
+ * the conv1 grid) -> dpc_stem_conv_wgrad_s2d.  Pooled extents: Hp = (H/2 - 1)/2 + 1, Wp likewise; rows = NB*T*Hp*Wp. */
+int dpc_stem_pool_supported(int H, int W);
+int dpc_stem_s2d_wpack(const float* w /*[64,3,1,7,7]*/, void* wp /*32768 bf16*/, void* stream);
+int dpc_stem_pool_fwd(const void* x2_hi, const void* x2_lo, const void* wp, const float* gamma, float* ypool /*[rows,64]*/,
+                      void* idx /*[rows,64] uint8*/, double* bn_ws /*128, nullable*/, int NB, int T, int H, int W, void* stream);
+int dpc_stem_pool_finalize(const float* ypool, void* idx, const float* mean, const float* rstd, const float* gamma,
+                           const float* beta, void* a_hi, void* a_lo, float* a_rows /*nullable*/, int64_t rows, void* stream);
+int dpc_stem_pool_bwd_reduce(const float* ypool, const float* dout, const void* idx, const float* mean, const float* rstd,
+                             double* ws /*128*/, float* dgamma, float* dbeta, int64_t rows, void* stream);
+int dpc_stem_pool_bwd(const void* x2_hi, const void* x2_lo, const void* wp, const float* dout, const void* idx,
+                      const float* mean, const float* rstd, const float* gamma, const double* ws, void* dy_hi, void* dy_lo,
+                      int NB, int T, int H, int W, void* stream);
 
 /* ---- BatchNorm3d(track_running_stats=False): batch statistics always ----------------------
  * replaces nn.BatchNorm3d at resnet_2d3d.py:55,59,91,95,212,243 (+ relu_ / `out += residual`

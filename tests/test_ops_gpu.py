@@ -381,3 +381,101 @@ def test_gru_cell_matches_oracle():
     XP = gru.xproj(xr, B * L_ * L_)
     hn, _ = gru.step(XP, 0, hr, B * L_ * L_, 0.0, 0, 0)
     assert rel(hn.cpu(), rows(ref).cpu()) < 2e-5
+
+
+@pytest.mark.parametrize('NB,T,H,W', [(2, 5, 64, 64), (2, 2, 128, 128), (1, 2, 64, 224), (3, 1, 36, 20), (1, 1, 90, 44),
+                                      (1, 1, 224, 224), (5, 5, 128, 128), (64, 5, 128, 128)])
+def test_stem_pool(NB, T, H, W):
+    """pooled stem (stem_pool.cu): conv1 + bn1 statistics + selected pooled value / window index, finalize into operand planes,
+    pooled-grid BatchNorm-backward sums, recomputing backward -> gradient planes on the conv1 grid.  One band (<= ~80 conv
+    columns) and two bands (W = 224), odd pooled extents, several frames per CTA, negative gamma (min-pool channels)."""
+    L = _lib()
+    assert L.stem_pool_supported(H, W) >= 1
+    g = torch.Generator(device='cuda').manual_seed(12)
+    x = torch.randn(NB, 3, T, H, W, device='cuda', generator=g)
+    w = torch.randn(64, 3, 1, 7, 7, device='cuda', generator=g) * 0.1
+    gamma = (torch.rand(64, device='cuda', generator=g) + 0.5) * torch.where(torch.rand(64, device='cuda', generator=g) < 0.25, -1.0, 1.0)
+    beta = torch.randn(64, device='cuda', generator=g) * 0.3
+    Ho, Wo = H // 2, W // 2
+    Hp, Wp = (Ho - 1) // 2 + 1, (Wo - 1) // 2 + 1
+    rows0, rows_p = NB * T * Ho * Wo, NB * T * Hp * Wp
+    bf = dict(dtype=torch.bfloat16, device='cuda')
+    x2h, x2l = torch.empty(NB, T, Ho, Wo, 16, **bf), torch.empty(NB, T, Ho, Wo, 16, **bf)
+    wp = torch.empty(32768, **bf)
+    L.stem_s2d_pack(x.data_ptr(), x2h.data_ptr(), x2l.data_ptr(), NB, T, H, W, _st())
+    L.stem_s2d_wpack(w.data_ptr(), wp.data_ptr(), _st())
+    ypool = torch.full((rows_p, 64), float('nan'), device='cuda')
+    idx = torch.full((rows_p, 64), 255, dtype=torch.uint8, device='cuda')
+    ws = torch.empty(128, dtype=torch.float64, device='cuda')
+    L.stem_pool_fwd(x2h.data_ptr(), x2l.data_ptr(), wp.data_ptr(), gamma.data_ptr(), ypool.data_ptr(), idx.data_ptr(),
+                    ws.data_ptr(), NB, T, H, W, _st())
+    torch.cuda.synchronize()
+    assert not torch.isnan(ypool).any() and int(idx.max()) <= 8
+    y0 = F.conv3d(x, w, None, (1, 2, 2), (0, 3, 3))                                   # [NB,64,T,Ho,Wo]
+    y0r = to_rows(y0)                                                                 # [rows0, 64]
+    ymax = float(y0.abs().max())
+    mean, rstd = torch.empty(64, device='cuda'), torch.empty(64, device='cuda')
+    L.bn_finalize(ws.data_ptr(), rows0, 64, 1e-5, mean.data_ptr(), rstd.data_ptr(), _st())
+    assert float((mean - y0r.double().mean(0)).abs().max()) < 1e-5 * ymax
+    assert rel(rstd, 1 / torch.sqrt(y0r.double().var(0, unbiased=False) + 1e-5)) < 1e-5
+    # the kept value is the conv output at the kept window index, and it is the window's max of sign(gamma) * y
+    y5 = y0r.view(NB * T, Ho, Wo, 64)
+    ypad = torch.full((NB * T, 2 * Hp + 1, 2 * Wp + 1, 64), float('nan'), device='cuda')
+    ypad[:, 1:Ho + 1, 1:Wo + 1] = y5
+    win = torch.stack([ypad[:, dh:dh + 2 * Hp:2, dw:dw + 2 * Wp:2] for dh in range(3) for dw in range(3)], -1)   # [NT,Hp,Wp,64,9]
+    kept = torch.gather(win, -1, idx.view(NB * T, Hp, Wp, 64, 1).long()).squeeze(-1)
+    assert not torch.isnan(kept).any()                                                # never a padding position
+    assert float((kept.reshape(-1, 64) - ypool).abs().max()) < 2e-5 * ymax
+    sgn = torch.where(gamma < 0, -1.0, 1.0)
+    wmax = torch.nan_to_num(win * sgn.view(1, 1, 1, 64, 1), nan=-1e30).max(-1).values
+    assert float((wmax.reshape(-1, 64) - ypool * sgn).abs().max()) < 2e-5 * ymax
+    # finalize: operand planes of relu(bn1(.)) on the pooled grid == maxpool(relu(bn1(conv1)))
+    ah, al = torch.empty(rows_p, 64, **bf), torch.empty(rows_p, 64, **bf)
+    arows = torch.empty(rows_p, 64, device='cuda')
+    L.stem_pool_finalize(ypool.data_ptr(), idx.data_ptr(), mean.data_ptr(), rstd.data_ptr(), gamma.data_ptr(), beta.data_ptr(),
+                         ah.data_ptr(), al.data_ptr(), arows.data_ptr(), rows_p, _st())
+    a_ref = F.max_pool3d(F.relu(F.batch_norm(y0, None, None, gamma, beta, True, 0.0, 1e-5)), (1, 3, 3), (1, 2, 2), (0, 1, 1))
+    assert tuple(a_ref.shape[2:]) == (T, Hp, Wp)
+    a_ref = to_rows(a_ref)
+    amax = float(a_ref.abs().max())
+    assert float((arows - a_ref).abs().max()) < 5e-5 * amax
+    assert float((ah.float() + al.float() - arows).abs().max()) < 2e-5 * amax
+    assert torch.equal(ah, arows.to(torch.bfloat16))
+    assert torch.equal((idx & 0x80) != 0, arows <= 0)                                 # ReLU-dead windows flagged
+    # backward: reference built with OUR window choice (a near-tie may legitimately pick the other position)
+    dout = torch.randn(rows_p, 64, device='cuda', generator=g)
+    k = idx.view(NB * T, Hp, Wp, 64)
+    d5 = dout.view(NB * T, Hp, Wp, 64).double()
+    gpad = torch.zeros(NB * T, 2 * Hp + 1, 2 * Wp + 1, 64, dtype=torch.float64, device='cuda')
+    for dh in range(3):
+        for dw in range(3):
+            gpad[:, dh:dh + 2 * Hp:2, dw:dw + 2 * Wp:2] += d5 * (k == dh * 3 + dw)
+    gg = gpad[:, 1:Ho + 1, 1:Wo + 1].reshape(rows0, 64)
+    assert float(gpad.sum() - gg.sum()) == 0.0 or abs(float(gpad.sum() - gg.sum())) < 1e-9 * float(gg.abs().sum())
+    xhat = (y0r.double() - mean.double()) * rstd.double()
+    sg, sgx = gg.sum(0), (gg * xhat).sum(0)
+    dy_ref = gamma.double() * rstd.double() * (gg - sg / rows0 - xhat * sgx / rows0)
+    ws2 = torch.empty(128, dtype=torch.float64, device='cuda')
+    dga, dbe = torch.empty(64, device='cuda'), torch.empty(64, device='cuda')
+    L.stem_pool_bwd_reduce(ypool.data_ptr(), dout.data_ptr(), idx.data_ptr(), mean.data_ptr(), rstd.data_ptr(), ws2.data_ptr(),
+                           dga.data_ptr(), dbe.data_ptr(), rows_p, _st())
+    assert float((dbe.double() - sg).abs().max()) < 5e-5 * float(sg.abs().max())
+    assert float((dga.double() - sgx).abs().max()) < 5e-5 * float(sgx.abs().max())
+    dyh = torch.full((rows0, 64), float('nan'), **bf)
+    dyl = torch.full((rows0, 64), float('nan'), **bf)
+    L.stem_pool_bwd(x2h.data_ptr(), x2l.data_ptr(), wp.data_ptr(), dout.data_ptr(), idx.data_ptr(), mean.data_ptr(),
+                    rstd.data_ptr(), gamma.data_ptr(), ws2.data_ptr(), dyh.data_ptr(), dyl.data_ptr(), NB, T, H, W, _st())
+    torch.cuda.synchronize()
+    dy = dyh.float() + dyl.float()
+    assert not torch.isnan(dy).any()
+    assert float((dy.double() - dy_ref).abs().max()) < 5e-5 * float(dy_ref.abs().max())
+    # the same backward with conv1's wgrad fused into the kernel (gradient tile in shared memory -> MN-major UMMA operand)
+    if L.stem_pool_supported(H, W) == 2:
+        wr = w.clone().requires_grad_(True)
+        F.conv3d(x, wr, None, (1, 2, 2), (0, 3, 3)).backward(from_rows(dy_ref.float(), NB, T, Ho, Wo))
+        dw = torch.full_like(w, float('nan'))
+        L.stem_pool_bwd_wgrad(x2h.data_ptr(), x2l.data_ptr(), wp.data_ptr(), dout.data_ptr(), idx.data_ptr(), mean.data_ptr(),
+                              rstd.data_ptr(), gamma.data_ptr(), ws2.data_ptr(), dw.data_ptr(), NB, T, H, W, _st())
+        torch.cuda.synchronize()
+        assert not torch.isnan(dw).any()
+        assert rel(dw, wr.grad) < 5e-5
