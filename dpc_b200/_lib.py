@@ -30,7 +30,8 @@ _SIGS = {
     'dpc_conv3d_wgrad': (c_int, [POINTER(ConvGeom), P, P, P, P]),
     'dpc_split_bf16': (c_int, [P, P, P, c_int64, P]),
     'dpc_pack_conv_weight_bf16': (c_int, [P, P, P, P, P, c_int, c_int, c_int, P]),
-    'dpc_gemm_nt_bf16x3_tc': (c_int, [c_int, c_int, c_int, P, P, P, P, P, c_int, P]),
+    'dpc_split_f16': (c_int, [P, P, P, c_int64, P]),
+    'dpc_gemm_nt_split_tc': (c_int, [c_int, c_int, c_int, P, P, P, P, c_int, P, c_int, P]),
     'dpc_conv3d_fwd_tc': (c_int, [POINTER(ConvGeom), P, P, P, P, P, P, P]),
     'dpc_conv3d_dgrad_tc': (c_int, [POINTER(ConvGeom), P, P, P, P, P, c_int, P]),
     'dpc_conv3d_dgrad_bnred_tc': (c_int, [POINTER(ConvGeom), P, P, P, P, P, c_int, P, P, P, P, P, P]),
@@ -67,6 +68,9 @@ _SIGS = {
     'dpc_gru_out': (c_int, [P, c_int, P, P, P, P, P, P, P, c_float, c_uint64, c_uint64, c_int64, c_int, P]),
     'dpc_gru_bwd_out': (c_int, [P, P, P, P, P, P, P, P, c_int64, c_int, P]),
     'dpc_gru_bwd_zr': (c_int, [P, P, P, P, P, P, P, c_int64, c_int, P]),
+    'dpc_head_chain_pack': (c_int, [P] * 10),
+    'dpc_head_chain_fwd': (c_int, [P] * 10 + [c_int, c_int, c_int, c_int, c_float, c_uint64] + [P] * 11),
+    'dpc_head_chain_bwd': (c_int, [P] * 6 + [c_int, c_int, c_int, c_int] + [P] * 13),
     'dpc_bias_relu': (c_int, [P, P, P, c_int, c_int64, c_int, P]),
     'dpc_relu_bwd': (c_int, [P, P, P, c_int, c_int64, P]),
     'dpc_nce_mask_fill': (c_int, [P, c_int, c_int, c_int, P]),

@@ -4,7 +4,11 @@
 //   D (fp32, TMEM) += sum over k-blocks  A_hi*B_hi + A_hi*B_lo + A_lo*B_hi          (3xBF16 split)
 //
 // * operands live in HBM as two bf16 planes (hi = bf16(x), lo = bf16(x - hi)): same bytes as fp32,
-//   ~16 mantissa bits -- what the 1e-3 parity bar needs (1-pass BF16/TF32 fail it);
+//   ~16 mantissa bits -- what the 1e-3 parity bar needs (1-pass BF16/TF32 fail it).  fp16 pairs
+//   (22 bits) would suit the O(1) forward values, but tcgen05 kind::f16 rejects mixed A / B formats (measured: an
+//   fp16 x bf16 descriptor raises "illegal instruction"), wgrad multiplies activations by gradients, and gradients
+//   need bf16's exponent range -- so activations stay bf16 pairs; only GEMMs whose operands are BOTH forward values
+//   (the score matmul) take fp16 pairs (dpc_gemm_nt_split_tc);
 // * an operand tile (positions x 64 channels of ONE filter tap) is ONE TMA box of the channels-last
 //   activation tensor [NB,T,H,W,C] at the tap-shifted coordinate; halo / zero padding is TMA
 //   out-of-bounds fill: no im2col buffer, no index arithmetic on the SM.  Strided convolutions read
@@ -21,6 +25,7 @@
 // Replaces nn.Conv3d fwd/bwd at backbone/resnet_2d3d.py:13-31,241-244 and torch.matmul at
 // dpc/model_3d.py:83.
 #include "tc_common.cuh"
+#include <cuda_fp16.h>
 #include <stdlib.h>
 
 namespace {
@@ -67,6 +72,7 @@ struct TcParams {
     // wgrad only
     int taps_full, splits, ktiles_per_split;
     int tap_group;             // taps per CTA (they share the dY tile; N = tap_group * BN)
+    int ab_f16;                // K-major kernels: 1 = both operands are fp16 pairs (score matmul), 0 = bf16 pairs
 };
 
 constexpr int A_TILE_BYTES = 128 * 128;            // 128 rows x 64 bf16
@@ -293,11 +299,12 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p, float* __r
     } else if (warp == 1) {
         if (elect_one()) {
             // instruction descriptor: D=f32, A=B=bf16, both K-major, N = BN, M = 128
-            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.BN >> 3) << 17) | ((128u >> 4) << 24);
+            const uint32_t fmt = (1u << 4) | (p.ab_f16 ? 0u : ((1u << 7) | (1u << 10)));     // D = f32; A = B: bf16 (1) or f16 (0)
+            const uint32_t idesc = fmt | ((uint32_t)(p.BN >> 3) << 17) | ((128u >> 4) << 24);
             // the B_hi and B_lo tiles are adjacent in a stage and so are the two accumulators: for BN <= 128 they
             // are one N = 2*BN operand / destination
             const bool wide = p.BN <= 128 && p.BN >= 16;
-            const uint32_t idesc2 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)((2 * p.BN) >> 3) << 17) | ((128u >> 4) << 24);
+            const uint32_t idesc2 = fmt | ((uint32_t)((2 * p.BN) >> 3) << 17) | ((128u >> 4) << 24);
             int s = 0; uint32_t ph = 0;
             for (int kb = 0; kb < num_kb; ++kb) {
                 mbar_wait(sp.full(s), ph);
@@ -448,8 +455,9 @@ conv_tc_persist_kernel(const __grid_constant__ TcMaps maps, const TcParams p, fl
         }
     } else if (warp == 1) {
         if (elect_one()) {
-            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.BN >> 3) << 17) | ((128u >> 4) << 24);
-            const uint32_t idesc2 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)((2 * p.BN) >> 3) << 17) | ((128u >> 4) << 24);
+            const uint32_t fmt = (1u << 4) | (p.ab_f16 ? 0u : ((1u << 7) | (1u << 10)));
+            const uint32_t idesc = fmt | ((uint32_t)(p.BN >> 3) << 17) | ((128u >> 4) << 24);
+            const uint32_t idesc2 = fmt | ((uint32_t)((2 * p.BN) >> 3) << 17) | ((128u >> 4) << 24);
             if (resident_b && my_tiles > 0) mbar_wait(w_full, 0);
             int s = 0; uint32_t ph = 0;
             for (int i = 0; i < my_tiles; ++i) {
@@ -561,6 +569,9 @@ __device__ __forceinline__ void halo_issue_tile(uint32_t a_lo, const uint32_t (&
     umma_commit(tmfull);
 }
 
+// RED: the epilogue also reduces the BatchNorm-backward sums of the consumer BN (hp.red, see BnRed) -- a separate
+// instantiation, so that the prefetch registers of that path do not cost the plain forward / dgrad kernel anything
+template <bool RED>
 __global__ void __launch_bounds__(320, 1)
 conv_tc_halo_kernel(const __grid_constant__ TcMaps maps, const HaloParams hp, float* __restrict__ y, int accumulate,
                     double* __restrict__ stats) {
@@ -582,7 +593,7 @@ conv_tc_halo_kernel(const __grid_constant__ TcMaps maps, const HaloParams hp, fl
     float* stat_smem = reinterpret_cast<float*>(smem_raw + (bar_base + 8u * (9 + 2 * hp.bstages) - smem_u32(smem_raw)));
     if (stats) {
         for (int i = threadIdx.x; i < 512; i += blockDim.x) stat_smem[i] = 0.f;
-        if (hp.red.y && threadIdx.x < HALO_BN) {
+        if (RED && threadIdx.x < HALO_BN) {
             stat_smem[512 + threadIdx.x] = hp.red.mean[threadIdx.x];
             stat_smem[768 + threadIdx.x] = hp.red.rstd[threadIdx.x];
         }
@@ -710,52 +721,71 @@ conv_tc_halo_kernel(const __grid_constant__ TcMaps maps, const HaloParams hp, fl
             const bool valid = h < hp.H && w < hp.W;
             const long long row = (long long)n * hp.out_sn + (long long)t * hp.out_st + (long long)h * hp.out_sh +
                                   (long long)w * hp.out_sw + hp.out_base;
+            // BatchNorm-backward fusion (BnRed): this lane's row of the consumer BN's input `y` and ReLU mask is requested
+            // BEFORE waiting for the accumulators, so the row-per-lane gather (32 separate 128-byte lines per warp
+            // instruction) overlaps the tile's MMAs instead of stalling the TMEM drain (measured without the prefetch:
+            // +1.28 ms on the layer1 dgrad against the 0.52 ms reduce pass it replaces)
+            float4 yv[8];
+            uint2 mk[8];
+            if (RED) {
+                const size_t off = (size_t)(valid ? row : 0) * hp.Co + c0;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    yv[j] = *reinterpret_cast<const float4*>(hp.red.y + off + 4 * j);
+                    mk[j] = hp.red.mask_hi ? *reinterpret_cast<const uint2*>(hp.red.mask_hi + off + 4 * j)
+                                           : make_uint2(0x3c003c00u, 0x3c003c00u);          // +1.0 (fp16): keep
+                }
+            }
             mbar_wait(tm_full(buf), ((uint32_t)i >> 1) & 1u);
             tc_fence_after();
-            uint32_t v[32], u[32];
-            tmem_ld32_nowait(td + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
-            tmem_ld32_nowait(tcx + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, u);
-            tmem_ld_wait();
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(tm_empty(buf));
-            if (hp.red.y) {
-                if (valid) {
-                    float4* dst = reinterpret_cast<float4*>(y + row * hp.Co + c0);
-    #pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        float4 o = make_float4(__uint_as_float(v[4 * j]) + __uint_as_float(u[4 * j]),
-                                               __uint_as_float(v[4 * j + 1]) + __uint_as_float(u[4 * j + 1]),
-                                               __uint_as_float(v[4 * j + 2]) + __uint_as_float(u[4 * j + 2]),
-                                               __uint_as_float(v[4 * j + 3]) + __uint_as_float(u[4 * j + 3]));
-                        if (accumulate) { const float4 c = dst[j]; o.x += c.x; o.y += c.y; o.z += c.z; o.w += c.w; }
-                        dst[j] = o;
-                        if (stats) {
-                            if (hp.red.y) {
-                                // BatchNorm-backward sums of the consumer BN (see BnRed)
-                                const size_t off = (size_t)row * hp.Co + c0 + 4 * j;
-                                const float4 yv = *reinterpret_cast<const float4*>(hp.red.y + off);
-                                uint2 mk = make_uint2(0x3f803f80u, 0x3f803f80u);
-                                if (hp.red.mask_hi) mk = *reinterpret_cast<const uint2*>(hp.red.mask_hi + off);
-                                const float* mr = stat_smem + 512 + c0 + 4 * j;
-                                const uint32_t h0 = mk.x & 0xffffu, h1 = mk.x >> 16, h2 = mk.y & 0xffffu, h3 = mk.y >> 16;
-                                const float g0 = ((h0 & 0x8000u) == 0u && (h0 & 0x7fffu) != 0u) ? o.x : 0.f;
-                                const float g1 = ((h1 & 0x8000u) == 0u && (h1 & 0x7fffu) != 0u) ? o.y : 0.f;
-                                const float g2 = ((h2 & 0x8000u) == 0u && (h2 & 0x7fffu) != 0u) ? o.z : 0.f;
-                                const float g3 = ((h3 & 0x8000u) == 0u && (h3 & 0x7fffu) != 0u) ? o.w : 0.f;
-                                rs[4 * j] += g0; rs[4 * j + 1] += g1; rs[4 * j + 2] += g2; rs[4 * j + 3] += g3;
-                                rq[4 * j] = fmaf(g0, (yv.x - mr[0]) * mr[256], rq[4 * j]);
-                                rq[4 * j + 1] = fmaf(g1, (yv.y - mr[1]) * mr[257], rq[4 * j + 1]);
-                                rq[4 * j + 2] = fmaf(g2, (yv.z - mr[2]) * mr[258], rq[4 * j + 2]);
-                                rq[4 * j + 3] = fmaf(g3, (yv.w - mr[3]) * mr[259], rq[4 * j + 3]);
-                            } else {
-                                rs[4 * j] += o.x; rs[4 * j + 1] += o.y; rs[4 * j + 2] += o.z; rs[4 * j + 3] += o.w;
-                                rq[4 * j] += o.x * o.x; rq[4 * j + 1] += o.y * o.y; rq[4 * j + 2] += o.z * o.z; rq[4 * j + 3] += o.w * o.w;
-                            }
+            if (RED) {
+                // two 16-column halves: keeps the accumulator registers (2 x 16) + the prefetched rows (48) + the running
+                // sums (64) inside the register file
+                float4* dst = reinterpret_cast<float4*>(y + (valid ? row : 0) * hp.Co + c0);
+#pragma unroll
+                for (int hf = 0; hf < 2; ++hf) {
+                    uint32_t v[16], u[16];
+                    tmem_ld16_nowait(td + ((uint32_t)(q * 32) << 16) + (uint32_t)(c0 + 16 * hf), v);
+                    tmem_ld16_nowait(tcx + ((uint32_t)(q * 32) << 16) + (uint32_t)(c0 + 16 * hf), u);
+                    tmem_ld_wait();
+                    if (hf == 1) {
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(tm_empty(buf));
+                    }
+                    if (valid) {
+#pragma unroll
+                        for (int jj = 0; jj < 4; ++jj) {
+                            const int j = 4 * hf + jj;
+                            float4 o = make_float4(__uint_as_float(v[4 * jj]) + __uint_as_float(u[4 * jj]),
+                                                   __uint_as_float(v[4 * jj + 1]) + __uint_as_float(u[4 * jj + 1]),
+                                                   __uint_as_float(v[4 * jj + 2]) + __uint_as_float(u[4 * jj + 2]),
+                                                   __uint_as_float(v[4 * jj + 3]) + __uint_as_float(u[4 * jj + 3]));
+                            if (accumulate) { const float4 c = dst[j]; o.x += c.x; o.y += c.y; o.z += c.z; o.w += c.w; }
+                            dst[j] = o;
+                            // BatchNorm-backward sums of the consumer BN (see BnRed)
+                            const float* mr = stat_smem + 512 + c0 + 4 * j;
+                            const uint32_t h0 = mk[j].x & 0xffffu, h1 = mk[j].x >> 16, h2 = mk[j].y & 0xffffu, h3 = mk[j].y >> 16;
+                            const float g0 = ((h0 & 0x8000u) == 0u && (h0 & 0x7fffu) != 0u) ? o.x : 0.f;
+                            const float g1 = ((h1 & 0x8000u) == 0u && (h1 & 0x7fffu) != 0u) ? o.y : 0.f;
+                            const float g2 = ((h2 & 0x8000u) == 0u && (h2 & 0x7fffu) != 0u) ? o.z : 0.f;
+                            const float g3 = ((h3 & 0x8000u) == 0u && (h3 & 0x7fffu) != 0u) ? o.w : 0.f;
+                            rs[4 * j] += g0; rs[4 * j + 1] += g1; rs[4 * j + 2] += g2; rs[4 * j + 3] += g3;
+                            rq[4 * j] = fmaf(g0, (yv[j].x - mr[0]) * mr[256], rq[4 * j]);
+                            rq[4 * j + 1] = fmaf(g1, (yv[j].y - mr[1]) * mr[257], rq[4 * j + 1]);
+                            rq[4 * j + 2] = fmaf(g2, (yv[j].z - mr[2]) * mr[258], rq[4 * j + 2]);
+                            rq[4 * j + 3] = fmaf(g3, (yv[j].w - mr[3]) * mr[259], rq[4 * j + 3]);
                         }
                     }
                 }
             } else {
+                uint32_t v[32], u[32];
+                tmem_ld32_nowait(td + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+                tmem_ld32_nowait(tcx + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, u);
+                tmem_ld_wait();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(tm_empty(buf));
                 float4 o[8];
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
@@ -1270,13 +1300,14 @@ int try_conv_halo(const void* src_hi, const void* src_lo, const void* wp_hi, con
     if (make_map(&maps.b_hi, wp_hi, 2, bd, bs, bb)) return -1;
     if (make_map(&maps.b_lo, wp_lo, 2, bd, bs, bb)) return -1;
     const size_t smem = 4 * (size_t)hp.patch_bytes + hp.bstages * b_stage + 8 * (9 + 2 * hp.bstages) + 4096 + 1024;
-    if (cudaFuncSetAttribute(conv_tc_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+    auto kern = (red && red->y) ? conv_tc_halo_kernel<true> : conv_tc_halo_kernel<false>;
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
         dpc_set_error("conv_tc_halo_kernel: cannot reserve %zu bytes of shared memory", smem);
         return -1;
     }
     const int sms = dpc_num_sms();
     const int grid = hp.total_tiles < sms ? hp.total_tiles : sms;
-    conv_tc_halo_kernel<<<grid, 320, smem, st>>>(maps, hp, y, accumulate, stats);
+    kern<<<grid, 320, smem, st>>>(maps, hp, y, accumulate, stats);
     dpc_count_launch(1);
     if (cudaError_t e = cudaGetLastError()) {
         dpc_set_error("conv_tc_halo_kernel launch: %s", cudaGetErrorString(e));
@@ -1378,6 +1409,7 @@ void set_tile_grid(TcParams& p, int NB, int T, int H, int W, int rows_max) {
     p.NB = NB; p.To = T; p.Ho = H; p.Wo = W;
 }
 
+template <bool F16>
 __global__ void split_bf16_kernel(const float4* __restrict__ src, uint2* __restrict__ hi, uint2* __restrict__ lo,
                                   long long n4) {
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
@@ -1386,10 +1418,17 @@ __global__ void split_bf16_kernel(const float4* __restrict__ src, uint2* __restr
         unsigned short h[4], l[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            __nv_bfloat16 bh = __float2bfloat16_rn(f[j]);
-            __nv_bfloat16 bl = __float2bfloat16_rn(f[j] - __bfloat162float(bh));
-            h[j] = __bfloat16_as_ushort(bh);
-            l[j] = __bfloat16_as_ushort(bl);
+            if (F16) {
+                const __half bh = __float2half_rn(f[j]);
+                const __half bl = __float2half_rn(f[j] - __half2float(bh));
+                h[j] = __half_as_ushort(bh);
+                l[j] = __half_as_ushort(bl);
+            } else {
+                __nv_bfloat16 bh = __float2bfloat16_rn(f[j]);
+                __nv_bfloat16 bl = __float2bfloat16_rn(f[j] - __bfloat162float(bh));
+                h[j] = __bfloat16_as_ushort(bh);
+                l[j] = __bfloat16_as_ushort(bl);
+            }
         }
         hi[i] = make_uint2((uint32_t)h[0] | ((uint32_t)h[1] << 16), (uint32_t)h[2] | ((uint32_t)h[3] << 16));
         lo[i] = make_uint2((uint32_t)l[0] | ((uint32_t)l[1] << 16), (uint32_t)l[2] | ((uint32_t)l[3] << 16));
@@ -1434,7 +1473,19 @@ extern "C" int dpc_split_bf16(const float* src, void* hi, void* lo, int64_t n, v
     long long n4 = n / 4;
     long long blocks = (n4 + 255) / 256;
     long long cap = (long long)dpc_num_sms() * 16;
-    split_bf16_kernel<<<(int)(blocks < cap ? blocks : cap), 256, 0, as_stream(stream)>>>(
+    split_bf16_kernel<false><<<(int)(blocks < cap ? blocks : cap), 256, 0, as_stream(stream)>>>(
+        (const float4*)src, (uint2*)hi, (uint2*)lo, n4);
+    DPC_LAUNCH_CHECK();
+    return DPC_OK;
+}
+
+// the same split into fp16 pairs (hi = fp16(x), lo = fp16(x - hi): ~22 mantissa bits): forward-value operands
+extern "C" int dpc_split_f16(const float* src, void* hi, void* lo, int64_t n, void* stream) {
+    DPC_REQUIRE(src && hi && lo && n > 0 && n % 4 == 0, "dpc_split_f16: bad args (n must be a multiple of 4)");
+    long long n4 = n / 4;
+    long long blocks = (n4 + 255) / 256;
+    long long cap = (long long)dpc_num_sms() * 16;
+    split_bf16_kernel<true><<<(int)(blocks < cap ? blocks : cap), 256, 0, as_stream(stream)>>>(
         (const float4*)src, (uint2*)hi, (uint2*)lo, n4);
     DPC_LAUNCH_CHECK();
     return DPC_OK;
@@ -1453,11 +1504,12 @@ extern "C" int dpc_pack_conv_weight_bf16(const float* w, void* wf_hi, void* wf_l
     return DPC_OK;
 }
 
-// C[M,N] (fp32, ldc = N) (+)= A[M,K] * B[N,K]^T from split-bf16 planes (K % 64 == 0)
-extern "C" int dpc_gemm_nt_bf16x3_tc(int M, int N, int K, const void* a_hi, const void* a_lo, const void* b_hi,
-                                     const void* b_lo, float* C, int accumulate, void* stream) {
-    DPC_REQUIRE(M > 0 && N > 0 && K > 0 && K % 64 == 0, "dpc_gemm_nt_bf16x3_tc: bad dims %d %d %d", M, N, K);
-    DPC_REQUIRE(a_hi && a_lo && b_hi && b_lo && C, "dpc_gemm_nt_bf16x3_tc: null pointer");
+// C[M,N] (fp32, ldc = N) (+)= A[M,K] * B[N,K]^T from split 16-bit planes (K % 64 == 0); f16 != 0: BOTH operands are fp16
+// pairs (dpc_split_f16; forward values of O(1) magnitude: ~22 mantissa bits), else bf16 pairs (dpc_split_bf16)
+extern "C" int dpc_gemm_nt_split_tc(int M, int N, int K, const void* a_hi, const void* a_lo, const void* b_hi,
+                                    const void* b_lo, int f16, float* C, int accumulate, void* stream) {
+    DPC_REQUIRE(M > 0 && N > 0 && K > 0 && K % 64 == 0, "dpc_gemm_nt_split_tc: bad dims %d %d %d", M, N, K);
+    DPC_REQUIRE(a_hi && a_lo && b_hi && b_lo && C, "dpc_gemm_nt_split_tc: null pointer");
     TcLaunch L;
     memset(&L.p, 0, sizeof(L.p));
     TcParams& p = L.p;
@@ -1465,6 +1517,7 @@ extern "C" int dpc_gemm_nt_bf16x3_tc(int M, int N, int K, const void* a_hi, cons
     fwd_taps(p.tT, 1, 1, 0); fwd_taps(p.tH, 1, 1, 0); fwd_taps(p.tW, 1, 1, 0);
     p.kH = p.kW = 1; p.sH = p.sW = 1; p.nviews = 1;
     p.cchunks = K / 64; p.Ksrc = K;
+    p.ab_f16 = f16 ? 1 : 0;
     set_tile_grid(p, 1, 1, 1, M, 128);
     p.Co = N; p.BN = pick_bn(N);
     set_stages(L, p.cchunks);

@@ -153,10 +153,10 @@ class ConvSite:
 # (the default product path); False = exact-fp32 CUDA-core kernels (reference precision, used by
 # tests to cross-check the tensor-core path).
 USE_TC = True
-# BatchNorm-backward reductions in the epilogue of the stride-1 dgrads that produce their input (dgrad_bnred).  Correct
-# (tests/test_tc_gpu.py) but OFF: measured at B = 128 the per-row gathers of mask / y in the TMEM epilogue cost more
-# than the separate coalesced reduce pass they replace (layer1 dgrad 1.06 -> 2.34 ms vs a 0.52 ms reduce; layer2
-# +0.38 vs 0.26; layer3 +0.31 vs 0.10).  Needs a smem-staged, column-contiguous epilogue to pay off.
+# BatchNorm-backward reductions in the epilogue of the stride-1 dgrads that produce their input (dgrad_bnred): False,
+# 'halo' (only the 64 -> 64 1x3x3 sites of layer1, whose halo-patch kernel prefetches the mask / y rows before it waits
+# for the accumulators) or True (every stride-1 site; measured slower on the tap-per-box kernels at B = 128: the per-row
+# gathers stall their 4-warp epilogue: layer2 +0.38 ms vs a 0.26 ms reduce pass, layer3 +0.31 vs 0.10).
 FUSE_BN_REDUCE = False
 # conv1 + bn1 + relu + maxpool without storing the conv1 output (stem_pool.cu); False = round-1 stem kernels
 STEM_POOL = True
@@ -164,12 +164,20 @@ STEM_POOL = True
 STEM_FUSE_WGRAD = True
 
 
+# Plane dtype of conv operands.  tcgen05 kind::f16 needs ONE input format per instruction and wgrad multiplies activations by
+# gradients (which need bf16's exponent range), so activations, weights and gradients are all bf16 pairs; only the score
+# matmul -- both operands forward values of O(1) magnitude -- runs on fp16 pairs (f16=True below).
+ACT = GRD = torch.bfloat16
+
+
 @_timed('split_bf16')
-def _split(x, st):
-    """fp32 rows -> (hi, lo) bf16 planes with hi + lo ~= x to ~2^-17"""
-    hi = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
-    lo = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
-    lib().split_bf16(ptr(x), ptr(hi), ptr(lo), x.numel(), st)
+def _split(x, st, f16=False):
+    """fp32 rows -> (hi, lo) 16-bit planes with hi + lo ~= x: bf16 pairs (~2^-17, fp32 range), or fp16 pairs (~2^-22) for
+    forward values that only ever meet other forward values (f16=True)"""
+    dt = torch.float16 if f16 else torch.bfloat16
+    hi = torch.empty(x.shape, dtype=dt, device=x.device)
+    lo = torch.empty(x.shape, dtype=dt, device=x.device)
+    (lib().split_f16 if f16 else lib().split_bf16)(ptr(x), ptr(hi), ptr(lo), x.numel(), st)
     return hi, lo
 
 
@@ -178,11 +186,10 @@ class TcConvSite(ConvSite):
     __slots__ = ('wfh', 'wfl', 'wdh', 'wdl')
 
     def pack(self, w, st):
-        bf = dict(dtype=torch.bfloat16, device=w.device)
-        self.wfh = torch.empty((self.Co, self.taps, self.Ci), **bf)
-        self.wfl = torch.empty((self.Co, self.taps, self.Ci), **bf)
-        self.wdh = torch.empty((self.Ci, self.taps, self.Co), **bf)
-        self.wdl = torch.empty((self.Ci, self.taps, self.Co), **bf)
+        self.wfh = torch.empty((self.Co, self.taps, self.Ci), dtype=ACT, device=w.device)
+        self.wfl = torch.empty((self.Co, self.taps, self.Ci), dtype=ACT, device=w.device)
+        self.wdh = torch.empty((self.Ci, self.taps, self.Co), dtype=GRD, device=w.device)
+        self.wdl = torch.empty((self.Ci, self.taps, self.Co), dtype=GRD, device=w.device)
         lib().pack_conv_weight_bf16(ptr(w), ptr(self.wfh), ptr(self.wfl), ptr(self.wdh), ptr(self.wdl),
                                     self.Co, self.Ci, self.taps, st)
 
@@ -232,6 +239,15 @@ class TcConvSite(ConvSite):
         g = self.geom
         return g.sT == 1 and g.sH == 1 and g.sW == 1
 
+    @property
+    def fuse_bnred(self):
+        """whether this site's dgrad should reduce the consumer BN's backward sums in its epilogue (FUSE_BN_REDUCE)"""
+        if not FUSE_BN_REDUCE or not self.stride1:
+            return False
+        g = self.geom
+        halo = (g.kT, g.kH, g.kW) == (1, 3, 3) and self.Ci == 64 and self.Co == 64
+        return halo or FUSE_BN_REDUCE is True
+
     @_timed('conv_wgrad')
     def wgrad(self, xp, dyp, st):
         g = self.geom
@@ -258,8 +274,7 @@ def _bn_apply(y, mean, rstd, gamma, beta, relu, rows, C, st, res=None, res_plane
     out = torch.empty_like(y) if want_rows else None
     planes = None
     if want_planes:
-        planes = (torch.empty(y.shape, dtype=torch.bfloat16, device=y.device),
-                  torch.empty(y.shape, dtype=torch.bfloat16, device=y.device))
+        planes = (torch.empty(y.shape, dtype=ACT, device=y.device), torch.empty(y.shape, dtype=ACT, device=y.device))
     r = rbn if rbn is not None else (None, None, None, None)
     rp = res_planes if (res is None and res_planes is not None) else (None, None)
     lib().bn_apply_fwd(ptr(y), ptr(mean), ptr(rstd), ptr(gamma), ptr(beta), ptr(res), ptr(rp[0]), ptr(rp[1]),
@@ -281,8 +296,7 @@ def _bn_bwd(dout, out, relu, y, mean, rstd, gamma, rows, C, st, want_g=False, ou
     dy = torch.empty_like(y) if want_rows else None
     planes = None
     if want_planes:
-        planes = (torch.empty(y.shape, dtype=torch.bfloat16, device=y.device),
-                  torch.empty(y.shape, dtype=torch.bfloat16, device=y.device))
+        planes = (torch.empty(y.shape, dtype=GRD, device=y.device), torch.empty(y.shape, dtype=GRD, device=y.device))
     g = torch.empty_like(y) if want_g else None
     fn = lib().bn_bwd_apply if fused else lib().bn_bwd
     fn(ptr(dout), ptr(out), ptr(out_hi) if out is None else None, 1 if relu else 0, ptr(y), ptr(mean),
@@ -339,7 +353,7 @@ def _stem_forward_unpooled(L, st, x, P, bn_state, training, running, network):
         ws0 = None if running else torch.empty(128, dtype=torch.float64, device=x.device)
         if H % 2 == 0 and W % 2 == 0:
             # space-to-depth planes + TMA halo-patch kernel (stem_s2d.cu)
-            bf = dict(dtype=torch.bfloat16, device=x.device)
+            bf = dict(dtype=ACT, device=x.device)
             x2 = (torch.empty((NB, T, H // 2, W // 2, 16), **bf), torch.empty((NB, T, H // 2, W // 2, 16), **bf))
             wp = torch.empty(32768, **bf)
             _timed('stem_fwd')(L.stem_s2d_pack)(ptr(x), ptr(x2[0]), ptr(x2[1]), NB, T, H, W, st)
@@ -389,7 +403,7 @@ def backbone_forward(network, x, P, need_ctx=True, bn_state=None, training=True)
     x2 = None
     Hp, Wp = _out_extent(Ho, 3, 2, 1), _out_extent(Wo, 3, 2, 1)
     rows_p = NB * T * Hp * Wp
-    bf = dict(dtype=torch.bfloat16, device=x.device)
+    bf = dict(dtype=ACT, device=x.device)
     pooled = USE_TC and STEM_POOL and L.stem_pool_supported(H, W) >= 1
     if pooled:
         # conv1 + bn1 + relu + maxpool with the conv1 output never stored (stem_pool.cu): the kernel keeps, per pooled
@@ -567,8 +581,8 @@ def _stem_backward_unpooled(L, st, ctx, dout, P, G):
     tc = USE_TC
     y0 = ctx['y0']
     dy0 = None if tc else torch.empty_like(y0)
-    dy0p = (torch.empty(y0.shape, dtype=torch.bfloat16, device=y0.device),
-            torch.empty(y0.shape, dtype=torch.bfloat16, device=y0.device)) if tc else (None, None)
+    dy0p = (torch.empty(y0.shape, dtype=GRD, device=y0.device),
+            torch.empty(y0.shape, dtype=GRD, device=y0.device)) if tc else (None, None)
     ws = torch.empty(128, dtype=torch.float64, device=y0.device)
     G['bn1.weight'], G['bn1.bias'] = _empty((64,), y0), _empty((64,), y0)
     _timed('stem_tail_bwd')(L.stem_tail_bwd)(ptr(y0), ptr(ctx['m0']), ptr(ctx['r0']), ptr(P['bn1.weight']),
@@ -660,7 +674,7 @@ def _backbone_backward(ctx, dout, P, side):
         G[p + '.conv2.weight'] = _wgrad_async(c2, rec['a1_op'], dy2, main, side)
         # conv2 is always stride 1: its dgrad also reduces bn1's backward sums in the epilogue (FUSE_BN_REDUCE)
         ws1 = None
-        if tc and FUSE_BN_REDUCE:
+        if tc and c2.fuse_bnred:
             da1, ws1 = c2.dgrad_bnred(dy2, st, rec['a1_op'][0], rec['y1'], rec['m1'], rec['r1'])
         else:
             da1 = c2.dgrad(dy2, st)
@@ -676,7 +690,7 @@ def _backbone_backward(ctx, dout, P, side):
             cd.dgrad(dyd, st, dx=dx)
             G[p + '.downsample.0.weight'] = _wgrad_async(cd, rec['xin_op'], dyd, main, side)
             del dyd, dydr, dydp
-        elif tc and FUSE_BN_REDUCE and bi > 0 and c1.stride1 and blocks[bi - 1].get('out_hi') is not None \
+        elif tc and c1.fuse_bnred and bi > 0 and blocks[bi - 1].get('out_hi') is not None \
                 and blocks[bi - 1]['spec']['block'] == 'basic':
             # dx = g + dgrad is the previous block's output gradient: reduce that block's bn2 sums here
             prev = blocks[bi - 1]
@@ -707,7 +721,7 @@ def _backbone_backward(ctx, dout, P, side):
                                                             NB, T, H, W, st)
             del dout
         else:
-            dy0p = (torch.empty((rows0, 64), dtype=torch.bfloat16, device=dev), torch.empty((rows0, 64), dtype=torch.bfloat16, device=dev))
+            dy0p = (torch.empty((rows0, 64), dtype=GRD, device=dev), torch.empty((rows0, 64), dtype=GRD, device=dev))
             _timed('stem_tail_bwd')(L.stem_pool_bwd)(ptr(x2[0]), ptr(x2[1]), ptr(ctx['wp']), ptr(dout), ptr(ctx['idx']), ptr(ctx['m0']),
                                                      ptr(ctx['r0']), ptr(P['bn1.weight']), ptr(ws), ptr(dy0p[0]), ptr(dy0p[1]),
                                                      NB, T, H, W, st)
@@ -804,10 +818,121 @@ class _Gru:
         return dx, dh
 
 
+# the recurrent head as ONE kernel per direction (head_chain.cu); False = the per-step GEMM + gate kernels above
+HEAD_CHAIN = True
+
+
+def _head_chain_ok(D):
+    return HEAD_CHAIN and USE_TC and D == 256
+
+
+def _head_forward_chain(z4, dims, B, N, pred_step, P, dropout_p, seed, need_ctx):
+    """pool/split -> head_chain_fwd (GRU aggregation + prediction loop, one launch) -> score GEMM"""
+    L = lib()
+    st = _stream()
+    To, Lh, Lw = dims
+    S, D = Lh * Lw, z4.shape[1]
+    NB, Tagg, R = B * N, N - pred_step, B * S
+    T7, M = N - 1, B * pred_step * S
+    finf_all = _empty((NB * S, D), z4)
+    feat = _empty((NB * S, D), z4)
+    L.pool_split_fwd(ptr(z4), ptr(finf_all), ptr(feat), NB, To, S, D, st)
+    g = 'agg.cell_list.0.'
+    Wz, Wr, Wo = P[g + 'update_gate.weight'], P[g + 'reset_gate.weight'], P[g + 'out_gate.weight']
+    W0, W2 = P['network_pred.0.weight'], P['network_pred.2.weight']
+    wt_zr, wt_o = _empty((2 * D, 2 * D), z4), _empty((2 * D, D), z4)
+    w0t, w2t = _empty((D, D), z4), _empty((D, D), z4)
+    L.head_chain_pack(ptr(Wz), ptr(Wr), ptr(Wo), ptr(W0), ptr(W2), ptr(wt_zr), ptr(wt_o), ptr(w0t), ptr(w2t), st)
+    XH, XO = _empty((T7 * R, 2 * D), z4), _empty((T7 * R, 2 * D), z4)
+    Z, Rg, O = _empty((T7 * R, D), z4), _empty((T7 * R, D), z4), _empty((T7 * R, D), z4)
+    Keep = _empty((T7 * R, D), z4) if dropout_p > 0 else None
+    U, Hp, Pp = _empty((pred_step * R, D), z4), _empty((pred_step * R, D), z4), _empty((pred_step * R, D), z4)
+    pred_rows = _empty((M, D), z4)
+    L.head_chain_fwd(ptr(feat), ptr(wt_zr), ptr(wt_o), ptr(w0t), ptr(w2t), ptr(P[g + 'update_gate.bias']),
+                     ptr(P[g + 'reset_gate.bias']), ptr(P[g + 'out_gate.bias']), ptr(P['network_pred.0.bias']),
+                     ptr(P['network_pred.2.bias']), B, N, S, pred_step, float(dropout_p), seed, ptr(XH), ptr(XO), ptr(Z), ptr(Rg),
+                     ptr(O), ptr(Keep), ptr(U), ptr(Hp), ptr(Pp), ptr(pred_rows), st)
+    finf_rows = _empty((M, D), z4)
+    L.gather_rows(ptr(finf_all), ptr(finf_rows), M, D, pred_step * S, N * S, Tagg * S, st)
+    score = _empty((M, M), z4)
+    pp, fp = _split(pred_rows, st, f16=True), _split(finf_rows, st, f16=True)
+    _timed('score_fwd')(L.gemm_nt_split_tc)(M, M, D, ptr(pp[0]), ptr(pp[1]), ptr(fp[0]), ptr(fp[1]), 1, ptr(score), 0, st)
+    ctx = None
+    if need_ctx:
+        ctx = dict(chain=True, B=B, N=N, P=pred_step, S=S, D=D, To=To, R=R, M=M, finf_all=finf_all, XH=XH, XO=XO, Z=Z, Rg=Rg,
+                   O=O, Keep=Keep, U=U, Hp=Hp, Pp=Pp, pred_rows=pred_rows, finf_rows=finf_rows)
+    return score, ctx
+
+
+def _wgrad_rows(x_rows, dy_rows, st):
+    """dW [Co, Ci] = dy_rows^T . x_rows (reduction over the rows) on the tcgen05 wgrad kernel"""
+    rows, Ci = x_rows.shape
+    Co = dy_rows.shape[1]
+    xp, dyp = _split(x_rows, st), _split(dy_rows, st)
+    geom = ConvGeom(1, 1, 1, rows, Ci, 1, 1, rows, Co, 1, 1, 1, 1, 1, 1, 0, 0, 0)
+    scratch = _empty((Co, Ci), x_rows)
+    dw = _empty((Co, Ci), x_rows)
+    lib().conv3d_wgrad_tc(geom, ptr(xp[0]), ptr(xp[1]), ptr(dyp[0]), ptr(dyp[1]), ptr(scratch), ptr(dw), st)
+    return dw
+
+
+def _head_backward_chain(ctx, dscore, P):
+    L = lib()
+    st = _stream()
+    B, N, Pn, S, D, To, R, M = (ctx[k] for k in ('B', 'N', 'P', 'S', 'D', 'To', 'R', 'M'))
+    NB, Tagg, T7 = B * N, N - Pn, N - 1
+    dev = dscore.device
+    g = 'agg.cell_list.0.'
+    dpred_rows = _empty((M, D), dscore)
+    dfinf_rows = _empty((M, D), dscore)
+    if M % 64 == 0:
+        dsp = _split(dscore, st)
+        ftp = _split(ctx['finf_rows'].t().contiguous(), st)
+        _timed('score_bwd')(L.gemm_nt_split_tc)(M, D, M, ptr(dsp[0]), ptr(dsp[1]), ptr(ftp[0]), ptr(ftp[1]), 0,
+                                                ptr(dpred_rows), 0, st)
+        pp = _split(ctx['pred_rows'], st)
+        geom = ConvGeom(1, 1, 1, M, D, 1, 1, M, M, 1, 1, 1, 1, 1, 1, 0, 0, 0)
+        scratch = _empty((M, D), dscore)
+        _timed('score_bwd')(L.conv3d_wgrad_tc)(geom, ptr(pp[0]), ptr(pp[1]), ptr(dsp[0]), ptr(dsp[1]), ptr(scratch),
+                                               ptr(dfinf_rows), st)
+        del dsp
+    else:                                          # K = M must be a multiple of 64 on the tensor-core GEMM: tiny test sizes
+        _gemm(0, 0, M, D, M, dscore, M, ctx['finf_rows'], D, dpred_rows, D, st)
+        _gemm(1, 0, M, D, M, dscore, M, ctx['pred_rows'], D, dfinf_rows, D, st)
+    dfinf_all = torch.zeros((NB * S, D), dtype=torch.float32, device=dev)
+    L.scatter_rows(ptr(dfinf_rows), ptr(dfinf_all), M, D, Pn * S, N * S, Tagg * S, 0, st)
+    dfeat = torch.zeros((NB * S, D), dtype=torch.float32, device=dev)
+    DZR, DO = _empty((T7 * R, 2 * D), dscore), _empty((T7 * R, D), dscore)
+    DP, DU = _empty((Pn * R, D), dscore), _empty((Pn * R, D), dscore)
+    L.head_chain_bwd(ptr(dpred_rows), ptr(P[g + 'update_gate.weight']), ptr(P[g + 'reset_gate.weight']),
+                     ptr(P[g + 'out_gate.weight']), ptr(P['network_pred.0.weight']), ptr(P['network_pred.2.weight']),
+                     B, N, S, Pn, ptr(ctx['XH']), ptr(ctx['Z']), ptr(ctx['Rg']), ptr(ctx['O']), ptr(ctx['Keep']), ptr(ctx['U']),
+                     ptr(ctx['Pp']), ptr(dfeat), ptr(DZR), ptr(DO), ptr(DP), ptr(DU), st)
+    G = {}
+    # weight gradients: reductions over (steps x rows) on the tensor-core wgrad kernel; biases: column sums
+    dWzr = _wgrad_rows(ctx['XH'], DZR, st)                                   # [2D (z | r), 2D (x | h)]
+    G[g + 'update_gate.weight'] = dWzr[:D].reshape(P[g + 'update_gate.weight'].shape)
+    G[g + 'reset_gate.weight'] = dWzr[D:].reshape(P[g + 'reset_gate.weight'].shape)
+    G[g + 'out_gate.weight'] = _wgrad_rows(ctx['XO'], DO, st).reshape(P[g + 'out_gate.weight'].shape)
+    G['network_pred.2.weight'] = _wgrad_rows(ctx['U'], DP, st).reshape(P['network_pred.2.weight'].shape)
+    G['network_pred.0.weight'] = _wgrad_rows(ctx['Hp'], DU, st).reshape(P['network_pred.0.weight'].shape)
+    bzr = torch.empty(2 * D, dtype=torch.float32, device=dev)
+    L.colsum(ptr(DZR), T7 * R, 2 * D, ptr(bzr), 0, st)
+    G[g + 'update_gate.bias'], G[g + 'reset_gate.bias'] = bzr[:D], bzr[D:]
+    for name, src, rows in ((g + 'out_gate.bias', DO, T7 * R), ('network_pred.2.bias', DP, Pn * R), ('network_pred.0.bias', DU, Pn * R)):
+        G[name] = torch.empty(D, dtype=torch.float32, device=dev)
+        L.colsum(ptr(src), rows, D, ptr(G[name]), 0, st)
+    dz4 = _empty((NB * To * S, D), dscore)
+    L.pool_split_bwd(ptr(ctx['finf_all']), ptr(dfinf_all), ptr(dfeat), ptr(dz4), NB, To, S, D, st)
+    return dz4, G
+
+
 @_timed('head_fwd')
 def head_forward(z4, dims, B, N, pred_step, P, dropout_p=0.0, seed=0, need_ctx=True):
     """z4: backbone output rows [B*N*To*S, D] (To temporal slices, S = L*L positions).
     Returns (score [M, M] with M = B*pred_step*S, ctx)."""
+    if _head_chain_ok(z4.shape[1]):
+        return _head_forward_chain(z4, dims, B, N, pred_step, P, dropout_p, seed, need_ctx)
     L = lib()
     st = _stream()
     To, Lh, Lw = dims
@@ -859,8 +984,8 @@ def head_forward(z4, dims, B, N, pred_step, P, dropout_p=0.0, seed=0, need_ctx=T
     L.gather_rows(ptr(finf_all), ptr(finf_rows), M, D, pred_step * S, N * S, Tagg * S, st)
     score = _empty((M, M), z4)
     if USE_TC:
-        pp, fp = _split(pred_rows, st), _split(finf_rows, st)
-        _timed('score_fwd')(L.gemm_nt_bf16x3_tc)(M, M, D, ptr(pp[0]), ptr(pp[1]), ptr(fp[0]), ptr(fp[1]), ptr(score), 0, st)
+        pp, fp = _split(pred_rows, st, f16=True), _split(finf_rows, st, f16=True)
+        _timed('score_fwd')(L.gemm_nt_split_tc)(M, M, D, ptr(pp[0]), ptr(pp[1]), ptr(fp[0]), ptr(fp[1]), 1, ptr(score), 0, st)
     else:
         _gemm(0, 1, M, M, D, pred_rows, D, finf_rows, D, score, M, st)
     ctx = None
@@ -873,6 +998,8 @@ def head_forward(z4, dims, B, N, pred_step, P, dropout_p=0.0, seed=0, need_ctx=T
 @_timed('head_bwd')
 def head_backward(ctx, dscore, P):
     """returns (dz4 rows [B*N*To*S, D], grads dict for HEAD_PARAM_NAMES)"""
+    if ctx.get('chain'):
+        return _head_backward_chain(ctx, dscore, P)
     L = lib()
     st = _stream()
     B, N, Pn, S, D, To, R, M = (ctx[k] for k in ('B', 'N', 'P', 'S', 'D', 'To', 'R', 'M'))
@@ -890,8 +1017,8 @@ def head_backward(ctx, dscore, P):
         dsp = _split(dscore, st)
         # dpred = dS . finf      -> NT GEMM against finf^T (tiny transpose: data movement only)
         ftp = _split(ctx['finf_rows'].t().contiguous(), st)
-        _timed('score_bwd')(L.gemm_nt_bf16x3_tc)(M, D, M, ptr(dsp[0]), ptr(dsp[1]), ptr(ftp[0]), ptr(ftp[1]),
-                                                 ptr(dpred_rows), 0, st)
+        _timed('score_bwd')(L.gemm_nt_split_tc)(M, D, M, ptr(dsp[0]), ptr(dsp[1]), ptr(ftp[0]), ptr(ftp[1]), 0,
+                                                ptr(dpred_rows), 0, st)
         # dfinf = dS^T . pred    -> the wgrad form (reduction over rows, both operands MN-major)
         pp = _split(ctx['pred_rows'], st)
         geom = ConvGeom(1, 1, 1, M, D, 1, 1, M, M, 1, 1, 1, 1, 1, 1, 0, 0, 0)

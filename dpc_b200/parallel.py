@@ -18,7 +18,8 @@ class FlatTrainer:
     After construction every `p.data` / `p.grad` is a view into one flat fp32 buffer, so
     `loss.backward()` accumulates straight into the all-reduce buffer."""
 
-    def __init__(self, module, lr=1e-3, weight_decay=1e-5, betas=(0.9, 0.999), eps=1e-8, process_group=None):
+    def __init__(self, module, lr=1e-3, weight_decay=1e-5, betas=(0.9, 0.999), eps=1e-8, process_group=None,
+                 distributed=True):
         params = [p for p in module.parameters() if p.requires_grad]
         if not params:
             raise ValueError('no trainable parameters')
@@ -41,7 +42,7 @@ class FlatTrainer:
         self.lr, self.wd, self.betas, self.eps = lr, weight_decay, betas, eps
         self.step_count = 0
         self.group = process_group
-        self.world = dist.get_world_size(process_group) if dist.is_available() and dist.is_initialized() else 1
+        self.world = dist.get_world_size(process_group) if (distributed and dist.is_available() and dist.is_initialized()) else 1
         if self.world > 1:
             # replicas start identical whatever each rank's RNG did (nn.DataParallel re-broadcasts rank 0's parameters
             # every forward, main.py:65; one process per GPU needs it once)

@@ -55,17 +55,20 @@ int dpc_conv3d_dgrad(const dpc_conv_geom* g, const float* dy, const float* wd, f
 int dpc_conv3d_wgrad(const dpc_conv_geom* g, const float* x, const float* dy, float* dwp, void* stream);
 
 /* ---- tcgen05 tensor-core path (3xBF16 split: fp32-equivalent to ~1e-5) ----------------------
- * Operands are pairs of bf16 planes: hi = bf16(x), lo = bf16(x - hi).  Same call sites as above
- * (conv3x3x3 / conv1x3x3 / 1x1x1 at resnet_2d3d.py:13-31,241-244) plus torch.matmul at
- * dpc/model_3d.py:83.  Channel counts must be multiples of 64. */
+ * Operands are pairs of bf16 planes: hi = bf16(x), lo = bf16(x - hi), multiplied as hi*hi + hi*lo + lo*hi into fp32 TMEM
+ * accumulators.  Same call sites as above (conv3x3x3 / conv1x3x3 / 1x1x1 at resnet_2d3d.py:13-31,241-244) plus
+ * torch.matmul at dpc/model_3d.py:83.  Channel counts must be multiples of 64.  tcgen05 kind::f16 needs ONE input format per
+ * instruction, and wgrad multiplies activations by gradients (which need bf16's exponent range), so activations are bf16
+ * pairs too; a GEMM whose operands are both forward values may use fp16 pairs (dpc_split_f16, ~22 mantissa bits). */
 int dpc_split_bf16(const float* src, void* hi, void* lo, int64_t n, void* stream);
+int dpc_split_f16(const float* src, void* hi, void* lo, int64_t n, void* stream);
 /* w [Co,Ci,taps] -> forward planes wf_* [Co][tap][Ci] and dgrad planes wd_* [Ci][tap][Co];
  * either pair may be NULL */
 int dpc_pack_conv_weight_bf16(const float* w, void* wf_hi, void* wf_lo, void* wd_hi, void* wd_lo,
                               int Co, int Ci, int taps, void* stream);
-/* C[M,N] (+)= A[M,K] * B[N,K]^T, fp32 out, K % 64 == 0 */
-int dpc_gemm_nt_bf16x3_tc(int M, int N, int K, const void* a_hi, const void* a_lo, const void* b_hi,
-                          const void* b_lo, float* C, int accumulate, void* stream);
+/* C[M,N] (+)= A[M,K] * B[N,K]^T, fp32 out, K % 64 == 0; f16: both operands are fp16 pairs (else bf16 pairs) */
+int dpc_gemm_nt_split_tc(int M, int N, int K, const void* a_hi, const void* a_lo, const void* b_hi, const void* b_lo,
+                         int f16, float* C, int accumulate, void* stream);
 /* forward, strides in {1,2}: y = conv(x planes [NB,Ti,Hi,Wi,Ci], wf planes [Co][taps][Ci]).
  * bn_ws (nullable, 2*Co doubles): the epilogue also accumulates the per-channel sum / sum of squares of y
  * (the BatchNorm batch statistics), to be turned into mean / rstd by dpc_bn_finalize. */
@@ -221,6 +224,29 @@ int dpc_gru_bwd_zr(const float* dhr, const float* h, const float* r, const float
 /* y = relu(x + b) (b nullable) and its backward */
 int dpc_bias_relu(const float* x, const float* b, float* y, int relu, int64_t R, int D, void* stream);
 int dpc_relu_bwd(const float* y, const float* dy, float* dx, int accumulate, int64_t n, void* stream);
+
+/* ---- recurrent head as one kernel per direction (head_chain.cu; feature size D = 256, ConvGRU kernel_size 1) ---------
+ * replaces ConvGRUCell.forward / ConvGRU.forward (backbone/convrnn.py:24-34,62-88) over the N - P aggregated blocks and the
+ * prediction loop of dpc/model_3d.py:62-72.  Rows r = b*S + s (R = B*S); T7 = N - 1 GRU steps run (N - P aggregate +
+ * P - 1 in the prediction loop; the step after the last prediction is dead work).  Gate weights W* are [D][2D] (x | h
+ * columns), network_pred weights [D][D].  Saved tensors are step-major:
+ *   XH [T7][R][2D] gate input (x | h), XO [T7][R][2D] out-gate input (x | h*r), Z / Rg / O / Keep [T7][R][D],
+ *   U / Hp / Pp [P][R][D] network_pred hidden (post-ReLU) / the state it was predicted from / the prediction,
+ *   pred_rows [B*P*S][D] the predictions in score-row order.
+ * Backward: dfeat [B*N*S][D] (only the aggregated blocks are written), DZR [T7][R][2D], DO [T7][R][D], DP / DU [P][R][D]
+ * = gradients of the pre-activations; the weight gradients are reductions over (steps x rows) of those against XH / XO /
+ * U / Hp (dpc_conv3d_wgrad_tc) and their column sums (dpc_colsum). */
+int dpc_head_chain_pack(const float* Wz, const float* Wr, const float* Wo, const float* W0, const float* W2,
+                        float* wt_zr /*[2D][2D]*/, float* wt_o /*[2D][D]*/, float* w0t, float* w2t, void* stream);
+int dpc_head_chain_fwd(const float* feat /*[B*N*S][D]*/, const float* wt_zr, const float* wt_o, const float* w0t,
+                       const float* w2t, const float* bz, const float* br, const float* bo, const float* b0, const float* b2,
+                       int B, int N, int S, int P, float p_drop, uint64_t seed, float* XH, float* XO, float* Z, float* Rg,
+                       float* O, float* Keep /*nullable when p_drop == 0*/, float* U, float* Hp, float* Pp, float* pred_rows,
+                       void* stream);
+int dpc_head_chain_bwd(const float* dpred_rows, const float* Wz, const float* Wr, const float* Wo, const float* W0,
+                       const float* W2, int B, int N, int S, int P, const float* XH, const float* Z, const float* Rg,
+                       const float* O, const float* Keep, const float* U, const float* Pp, float* dfeat, float* DZR, float* DO,
+                       float* DP, float* DU, void* stream);
 
 /* ---- NCE score / mask / cross-entropy -------------------------------------------------------
  * mask: closed form of the Python loops at dpc/model_3d.py:86-96 (values {1,-1,-3,0}, contiguous).

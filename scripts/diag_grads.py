@@ -20,7 +20,7 @@ for K in (256, 4096, 65536):
     B = torch.rand(N, K, device='cuda', generator=g) + 0.5
     ah, al = E._split(A, st); bh, bl = E._split(B, st)
     C = torch.empty(M, N, device='cuda')
-    L.gemm_nt_bf16x3_tc(M, N, K, ah.data_ptr(), al.data_ptr(), bh.data_ptr(), bl.data_ptr(), C.data_ptr(), 0, st)
+    L.gemm_nt_split_tc(M, N, K, ah.data_ptr(), al.data_ptr(), bh.data_ptr(), bl.data_ptr(), 0, C.data_ptr(), 0, st)
     ref = A.double() @ B.double().t()
     ref16 = (ah.double() + al.double()) @ (bh.double() + bl.double()).t()
     c32 = A @ B.t()

@@ -479,3 +479,38 @@ def test_stem_pool(NB, T, H, W):
         torch.cuda.synchronize()
         assert not torch.isnan(dw).any()
         assert rel(dw, wr.grad) < 5e-5
+
+
+@pytest.mark.parametrize('B,L_,p', [(3, 2, 0.0), (4, 4, 0.1), (5, 7, 0.1)])
+def test_head_chain_matches_stepwise(B, L_, p):
+    """head_chain.cu (GRU aggregation + prediction loop as one kernel per direction, tensor-core weight gradients) against the
+    per-step GEMM + gate kernels (which tests/test_parity_gpu.py pins to the oracle): same dropout stream, so train mode too.
+    L_ = 7 is the 224^2 extent (rows per clip 49: the last 16-row CTA is partial)."""
+    from dpc_b200 import engine as E
+    from oracle import dpc_oracle as O
+    N, P_, D, To = 8, 3, 256, 2
+    S = L_ * L_
+    sd = O.synthetic_state_dict('resnet18', 17)
+    P = {k: v.cuda() for k, v in sd.items() if k.startswith('agg.cell_list') or k.startswith('network_pred')}
+    g = torch.Generator(device='cuda').manual_seed(18)
+    z4 = torch.randn(B * N * To * S, D, device='cuda', generator=g)
+    M = B * P_ * S
+    dscore = torch.randn(M, M, device='cuda', generator=g) / M
+    out = {}
+    for chain in (False, True):
+        E.HEAD_CHAIN = chain
+        try:
+            score, ctx = E.head_forward(z4, (To, L_, L_), B, N, P_, P, dropout_p=p, seed=4242)
+            assert bool(ctx.get('chain', False)) == chain
+            dz4, G = E.head_backward(ctx, dscore.clone(), P)
+            torch.cuda.synchronize()
+        finally:
+            E.HEAD_CHAIN = True
+        out[chain] = (score, dz4, G)
+    s0, d0, G0 = out[False]
+    s1, d1, G1 = out[True]
+    assert rel(s1, s0) < 1e-5
+    assert rel(d1, d0) < 2e-5
+    for k in E.HEAD_PARAM_NAMES:
+        assert G1[k].shape == G0[k].shape, k
+        assert rel(G1[k], G0[k]) < 1e-4, (k, rel(G1[k], G0[k]))

@@ -192,7 +192,10 @@ def test_train_mode_dropout_matches_oracle_with_same_masks():
     rows, dims, _ = E.backbone_forward(network, block.view(B * N, 3, 5, img, img).cuda().contiguous(), bb, need_ctx=False)
     score, ctx = E.head_forward(rows, dims, B, N, P, Pd, dropout_p=0.1, seed=1234)
     L = dims[1]
-    keeps = [sv['keep'] for sv in ctx['steps']] + [r['gru']['keep'] for r in ctx['psteps'] if 'gru' in r]
+    if ctx.get('chain'):                    # head_chain.cu: keep masks of the N - 1 live GRU steps, step-major
+        keeps = list(ctx['Keep'].view(N - 1, B * L * L, 256).unbind(0))
+    else:
+        keeps = [sv['keep'] for sv in ctx['steps']] + [r['gru']['keep'] for r in ctx['psteps'] if 'gru' in r]
     assert len(keeps) == (N - P) + (P - 1)
     frac = float(torch.stack(keeps).eq(0).float().mean())
     assert 0.07 < frac < 0.13                                        # p = 0.1

@@ -31,11 +31,13 @@ def rel(a, b):
     return float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
 
 
-def split(x):
+def split(x, f16=False):
+    """bf16 pairs (dpc_split_bf16: every conv operand) or fp16 pairs (dpc_split_f16: forward-value-only GEMMs)"""
     x = x.contiguous()
-    hi = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
-    lo = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
-    _lib().split_bf16(x.data_ptr(), hi.data_ptr(), lo.data_ptr(), x.numel(), _st())
+    dt = torch.float16 if f16 else torch.bfloat16
+    hi = torch.empty(x.shape, dtype=dt, device=x.device)
+    lo = torch.empty(x.shape, dtype=dt, device=x.device)
+    (_lib().split_f16 if f16 else _lib().split_bf16)(x.data_ptr(), hi.data_ptr(), lo.data_ptr(), x.numel(), _st())
     return hi, lo
 
 
@@ -47,33 +49,42 @@ def from_rows(r, NB, T, H, W):
     return r.view(NB, T, H, W, -1).permute(0, 4, 1, 2, 3).contiguous()
 
 
-def test_split_bf16():
+def test_split_planes():
     g = torch.Generator(device='cuda').manual_seed(1)
     x = torch.randn(1 << 16, device='cuda', generator=g) * 3
-    hi, lo = split(x)
+    hi, lo = split(x)                                                 # bf16 pairs: 16 mantissa bits
     rec = hi.float() + lo.float()
     assert float(((rec - x).abs() / x.abs().clamp_min(1e-20)).max()) < 2.0 ** -15
     assert torch.equal(hi, x.to(torch.bfloat16))
+    hi, lo = split(x, f16=True)                                       # fp16 pairs: 22 mantissa bits (values O(1))
+    rec = hi.float() + lo.float()
+    big = x.abs() > 1e-2
+    assert float(((rec - x).abs() / x.abs())[big].max()) < 2.0 ** -20
+    assert float((rec - x).abs().max()) < 2.0 ** -20 * 16
+    assert torch.equal(hi, x.to(torch.float16))
 
 
 @pytest.mark.parametrize('M,N,K', [(128, 256, 64), (256, 256, 256), (1024, 768, 256), (200, 100, 128),
                                    (1617, 1617, 256), (6144, 512, 256)])
-def test_gemm_nt_bf16x3(M, N, K):
+@pytest.mark.parametrize('f16', [0, 1])
+def test_gemm_nt_split(M, N, K, f16):
+    """f16 = 1: both operands fp16 pairs (the score matmul's forward: 5e-6); 0: bf16 pairs (its backward GEMMs: 5e-5)"""
     L = _lib()
     g = torch.Generator(device='cuda').manual_seed(2)
     A = torch.randn(M, K, device='cuda', generator=g)
     B = torch.randn(N, K, device='cuda', generator=g)
-    ah, al = split(A)
-    bh, bl = split(B)
+    ah, al = split(A, f16=bool(f16))
+    bh, bl = split(B, f16=bool(f16))
     C = torch.full((M, N), float('nan'), device='cuda')
-    L.gemm_nt_bf16x3_tc(M, N, K, ah.data_ptr(), al.data_ptr(), bh.data_ptr(), bl.data_ptr(), C.data_ptr(), 0, _st())
+    L.gemm_nt_split_tc(M, N, K, ah.data_ptr(), al.data_ptr(), bh.data_ptr(), bl.data_ptr(), f16, C.data_ptr(), 0, _st())
     torch.cuda.synchronize()
     ref = A.double() @ B.double().t()
     assert not torch.isnan(C).any()
-    assert rel(C, ref) < 5e-5
+    tol = 5e-6 if f16 else 5e-5
+    assert rel(C, ref) < tol
     C2 = torch.ones(M, N, device='cuda')
-    L.gemm_nt_bf16x3_tc(M, N, K, ah.data_ptr(), al.data_ptr(), bh.data_ptr(), bl.data_ptr(), C2.data_ptr(), 1, _st())
-    assert rel(C2, ref + 1) < 5e-5
+    L.gemm_nt_split_tc(M, N, K, ah.data_ptr(), al.data_ptr(), bh.data_ptr(), bl.data_ptr(), f16, C2.data_ptr(), 1, _st())
+    assert rel(C2, ref + 1) < tol
 
 
 CASES = [
