@@ -287,8 +287,9 @@ def _record(res):
 # scripts/grad_table.py, fp64 oracle on the same GPU as the arbiter): the error does NOT fall with the batch -- it is the
 # forward rounding level amplified ~100-300x by the network's conditioning (BatchNorm backward projections, the CE
 # softmax), for ANY arithmetic: the exact-fp32 oracle is 2-5e-3 from fp64 at every B in {2, 8, 32, 128}, this path
-# (3xBF16 operands, forward error 6-9e-5 vs the oracle's 8e-6) 0.8-1.5e-2, a constant ~4x ratio.  Bounds = measured x 1.7.
-GRAD_TOL_ALL_B128, GRAD_TOL_WORST_B128 = 1.5e-2, 2.5e-2
+# (3xBF16 operands, forward error 6-9e-5 vs the oracle's 8e-6) 0.8-1.5e-2 (worst tensor 1.1-2.0e-2), a constant ~4x ratio.
+# Bounds = the largest measurement x 1.7.
+GRAD_TOL_ALL_B128, GRAD_TOL_WORST_B128 = 2.5e-2, 3.5e-2
 
 
 def test_config2_exact_train_step_vs_oracle_on_device():
