@@ -225,9 +225,20 @@ def run_stock_cuda(a, world, steps, warmup=2):
         torch.cuda.synchronize(d)
     wall = (time.perf_counter() - t0) * 1e3 / steps
     ms = e0.elapsed_time(e1) / steps
-    return {'clips_s': B / (ms / 1e3), 'ms_per_step': ms, 'wall_ms_per_step': wall, 'steps': steps, 'warmup': warmup,
-            'global_batch': B, 'n_gpus': world, 'impl': impl, 'loss': float(loss),
-            'peak_mem_gb': torch.cuda.max_memory_allocated(dev) / 1e9}
+    out = {'clips_s': B / (ms / 1e3), 'ms_per_step': ms, 'wall_ms_per_step': wall, 'steps': steps, 'warmup': warmup,
+           'global_batch': B, 'n_gpus': world, 'impl': impl, 'loss': float(loss.detach()),
+           'peak_mem_gb': torch.cuda.max_memory_allocated(dev) / 1e9}
+    if world > 1:
+        # nn.DataParallel rebuilds the 6-D mask with Python loops in every replica on every step (model_3d.py:86-96: the
+        # replicas are throw-away copies, so `self.mask` never survives) and re-broadcasts the parameters: the reference's
+        # own multi-GPU path is slower than its single-GPU path.  Also report the single-GPU rate, i.e. what an ideal
+        # data-parallel launcher would multiply by `world`.
+        del step, x
+        torch.cuda.empty_cache()
+        one = run_stock_cuda(a, 1, steps, warmup)
+        out['single_gpu_clips_s'] = one.get('clips_s')
+        out['ideal_ddp_clips_s'] = one['clips_s'] * world if one.get('clips_s') else None
+    return out
 
 
 def conv_family_flops(network, NB, T, H, W):
@@ -411,6 +422,15 @@ def run_b200(a, rank, local_rank, world):
                     'algorithmic_flops_per_launch': fl3, 'algorithmic_bytes_per_launch': 2 * rows3 * 256 * 4 + 27 * 256 * 256 * 4,
                     'peak_source': how + ' bf16_tflops_sustained (kernel timed inside the step)', 'mma_passes': 3,
                     'executed_tflops': 3 * a3, 'family': family, 'ncu': ev}
+            # the score matmul (dpc/model_3d.py:79-83) is bound by its fp32 output write: M^2 * 4 bytes (+ the operands)
+            sc = [ms for _, ms in timer.calls('score_fwd')]
+            if sc:
+                Msc = B * a.pred_step * ((a.img_dim + 31) // 32) ** 2
+                by = Msc * Msc * 4.0 + 2 * Msc * 256 * 4.0
+                gbs = by / (sc[0] / 1e3) / 1e9
+                roof['score_matmul'] = {'kernel': 'score matmul forward [M,256] x [256,M] -> fp32 [M,M], fp16-pair operands',
+                                        'bound': 'hbm', 'M': Msc, 'ms': sc[0], 'algorithmic_bytes': by, 'achieved': gbs, 'peak': hbm,
+                                        'unit': 'GB/s', 'frac': gbs / hbm, 'tflops_algorithmic': 2.0 * Msc * Msc * 256 / (sc[0] / 1e3) / 1e12}
         else:
             roof = dict(family, bound='tensor', peak=tf, unit='TFLOP/s', traffic=None, mma_passes=3,
                         peak_source=how + ' bf16_tflops_sustained', ncu=ev)
@@ -452,7 +472,8 @@ def run_b200(a, rank, local_rank, world):
                 'cpu_baseline': cpu, 'kernel_families_ms': fam, 'loss': last_loss,
                 'allreduce_ms': allreduce_ms, 'rank_ms_per_step': rank_ms, 'conv_sites_ms': sites,
                 'stock_cuda': stock,
-                'vs_stock_cuda': (value / stock['clips_s']) if stock and stock.get('clips_s') else None}
+                'vs_stock_cuda': (value / stock['clips_s']) if stock and stock.get('clips_s') else None,
+                'vs_stock_cuda_ideal_ddp': (value / stock['ideal_ddp_clips_s']) if stock and stock.get('ideal_ddp_clips_s') else None}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -30,6 +30,7 @@ _SIGS = {
     'dpc_conv3d_wgrad': (c_int, [POINTER(ConvGeom), P, P, P, P]),
     'dpc_split_bf16': (c_int, [P, P, P, c_int64, P]),
     'dpc_pack_conv_weight_bf16': (c_int, [P, P, P, P, P, c_int, c_int, c_int, P]),
+    'dpc_score_matmul_tc': (c_int, [c_int, c_int, c_int, P, P, P, P, c_int, P, P]),
     'dpc_split_f16': (c_int, [P, P, P, c_int64, P]),
     'dpc_gemm_nt_split_tc': (c_int, [c_int, c_int, c_int, P, P, P, P, c_int, P, c_int, P]),
     'dpc_conv3d_fwd_tc': (c_int, [POINTER(ConvGeom), P, P, P, P, P, P, P]),

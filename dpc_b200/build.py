@@ -35,6 +35,7 @@ def build(force=False, verbose=False):
         obj = os.path.join(bdir, os.path.basename(src)[:-3] + '.o')
         objs.append(obj)
         deps = [src] + [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith('.cuh')]
+        deps.append(os.path.join(os.path.dirname(HERE), 'include', 'dpc_b200.h'))     # common.cuh includes the ABI header
         if not force and os.path.exists(obj) and all(os.path.getmtime(obj) > os.path.getmtime(d) for d in deps):
             continue
         cmd = [NVCC] + FLAGS + (['-Xptxas', '-v'] if verbose else []) + ['-c', src, '-o', obj]

@@ -565,11 +565,17 @@ def backbone_backward(ctx, dout, P):
     caller = torch.cuda.current_stream()
     chain = _chain_stream(dout.device)
     side = _side_stream(dout.device)
+    # Stream invariant: every kernel below runs on `chain` (dgrad / BatchNorm backward) or `side` (weight gradients); both
+    # are ordered after the caller's stream here and joined back into it before returning, so the caller may use G (and
+    # free the saved activations) in plain stream order.  The gradients were allocated while `chain` / `side` were current:
+    # record the caller's stream on them so the caching allocator does not recycle their memory early.
     chain.wait_stream(caller)
     with torch.cuda.stream(chain):
         G = _backbone_backward(ctx, dout, P, side)
     dout.record_stream(chain)
     caller.wait_stream(chain)
+    for t in G.values():
+        t.record_stream(caller)
     return G
 
 
@@ -856,7 +862,7 @@ def _head_forward_chain(z4, dims, B, N, pred_step, P, dropout_p, seed, need_ctx)
     L.gather_rows(ptr(finf_all), ptr(finf_rows), M, D, pred_step * S, N * S, Tagg * S, st)
     score = _empty((M, M), z4)
     pp, fp = _split(pred_rows, st, f16=True), _split(finf_rows, st, f16=True)
-    _timed('score_fwd')(L.gemm_nt_split_tc)(M, M, D, ptr(pp[0]), ptr(pp[1]), ptr(fp[0]), ptr(fp[1]), 1, ptr(score), 0, st)
+    _timed('score_fwd')(L.score_matmul_tc)(M, M, D, ptr(pp[0]), ptr(pp[1]), ptr(fp[0]), ptr(fp[1]), 1, ptr(score), st)
     ctx = None
     if need_ctx:
         ctx = dict(chain=True, B=B, N=N, P=pred_step, S=S, D=D, To=To, R=R, M=M, finf_all=finf_all, XH=XH, XO=XO, Z=Z, Rg=Rg,

@@ -85,8 +85,6 @@ class LC(nn.Module):
         self.last_duration = int(math.ceil(seq_len / 4))
         self.last_size = int(math.ceil(sample_size / 32))
         self.backbone, self.param = select_resnet(network, track_running_stats=True)
-        if self.param['feature_size'] != engine.FEATURE_SIZE:
-            raise NotImplementedError('LC over the Bottleneck networks (r50+) is not built / pinned yet; use resnet18 or resnet34')
         self.param['num_layers'] = 1
         self.param['hidden_size'] = self.param['feature_size']
         print('=> using ConvRNN, kernel_size = 1')

@@ -69,6 +69,10 @@ int dpc_pack_conv_weight_bf16(const float* w, void* wf_hi, void* wf_lo, void* wd
 /* C[M,N] (+)= A[M,K] * B[N,K]^T, fp32 out, K % 64 == 0; f16: both operands are fp16 pairs (else bf16 pairs) */
 int dpc_gemm_nt_split_tc(int M, int N, int K, const void* a_hi, const void* a_lo, const void* b_hi, const void* b_lo,
                          int f16, float* C, int accumulate, void* stream);
+/* the score matmul of dpc/model_3d.py:83 on a persistent, A-resident schedule (score_tc.cu): C[M,N] = A[M,256] . B[N,256]^T,
+ * K must be 256; f16 as above */
+int dpc_score_matmul_tc(int M, int N, int K, const void* a_hi, const void* a_lo, const void* b_hi, const void* b_lo, int f16,
+                        float* C, void* stream);
 /* forward, strides in {1,2}: y = conv(x planes [NB,Ti,Hi,Wi,Ci], wf planes [Co][taps][Ci]).
  * bn_ws (nullable, 2*Co doubles): the epilogue also accumulates the per-channel sum / sum of squares of y
  * (the BatchNorm batch statistics), to be turned into mean / rstd by dpc_bn_finalize. */

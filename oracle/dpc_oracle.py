@@ -422,8 +422,6 @@ def cpu_train_step_time(network='resnet18', img=128, batch=4, steps=3, warmup=1,
 # --------------------------------------------------------------------------------------------
 def lc_param_shapes(network, num_class=101):
     """parameters AND buffers of LC in state_dict order (track_running_stats=True everywhere)"""
-    if network in BOTTLENECK:
-        raise NotImplementedError('the LC restatement covers the BasicBlock networks (resnet18 / resnet34) only')
     sh = OrderedDict()
 
     def bn(prefix, c):
@@ -434,13 +432,21 @@ def lc_param_shapes(network, num_class=101):
     for b in backbone_spec(network):
         p = 'backbone.' + b['name']
         k = (3, 3, 3) if b['is3d'] else (1, 3, 3)
-        sh[p + '.conv1.weight'] = (b['planes'], b['inplanes']) + k
-        bn(p + '.bn1', b['planes'])
-        sh[p + '.conv2.weight'] = (b['planes'], b['planes']) + k
-        bn(p + '.bn2', b['planes'])
+        if b['block'] == 'bottleneck':                              # resnet_2d3d.py:123-137,165-179
+            sh[p + '.conv1.weight'] = (b['planes'], b['inplanes'], 1, 1, 1)
+            bn(p + '.bn1', b['planes'])
+            sh[p + '.conv2.weight'] = (b['planes'], b['planes']) + k
+            bn(p + '.bn2', b['planes'])
+            sh[p + '.conv3.weight'] = (b['outplanes'], b['planes'], 1, 1, 1)
+            bn(p + '.bn3', b['outplanes'])
+        else:
+            sh[p + '.conv1.weight'] = (b['planes'], b['inplanes']) + k
+            bn(p + '.bn1', b['planes'])
+            sh[p + '.conv2.weight'] = (b['planes'], b['planes']) + k
+            bn(p + '.bn2', b['planes'])
         if b['downsample']:
-            sh[p + '.downsample.0.weight'] = (b['planes'], b['inplanes'], 1, 1, 1)
-            bn(p + '.downsample.1', b['planes'])
+            sh[p + '.downsample.0.weight'] = (b['outplanes'], b['inplanes'], 1, 1, 1)
+            bn(p + '.downsample.1', b['outplanes'])
     D = feature_size(network)
     for cell in ('agg.ConvGRUCell_00', 'agg.cell_list.0'):
         for g in ('reset_gate', 'update_gate', 'out_gate'):
@@ -507,8 +513,13 @@ def lc_forward(block, sd, network='resnet18', training=False, new_stats=None):
             s1, pad, sds = (b['stride'],) * 3, (1, 1, 1), (b['stride'],) * 3
         else:
             s1, pad, sds = (1, b['stride'], b['stride']), (0, 1, 1), (1, b['stride'], b['stride'])
-        out = F.relu(bn(F.conv3d(x, sd[p + '.conv1.weight'], None, s1, pad), p + '.bn1'))
-        out = bn(F.conv3d(out, sd[p + '.conv2.weight'], None, 1, pad), p + '.bn2')
+        if b['block'] == 'bottleneck':                              # Bottleneck2d / 3d.forward, resnet_2d3d.py:139-158,181-200
+            out = F.relu(bn(F.conv3d(x, sd[p + '.conv1.weight'], None, 1, 0), p + '.bn1'))
+            out = F.relu(bn(F.conv3d(out, sd[p + '.conv2.weight'], None, s1, pad), p + '.bn2'))
+            out = bn(F.conv3d(out, sd[p + '.conv3.weight'], None, 1, 0), p + '.bn3')
+        else:
+            out = F.relu(bn(F.conv3d(x, sd[p + '.conv1.weight'], None, s1, pad), p + '.bn1'))
+            out = bn(F.conv3d(out, sd[p + '.conv2.weight'], None, 1, pad), p + '.bn2')
         res = bn(F.conv3d(x, sd[p + '.downsample.0.weight'], None, sds, 0), p + '.downsample.1') if b['downsample'] else x
         out = out + res
         x = F.relu(out) if b['final_relu'] else out

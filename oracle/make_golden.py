@@ -174,7 +174,10 @@ def make_lc(network='resnet18', img=64, B=3, seed_w=51, seed_x=52, num_class=101
 
 
 if __name__ == '__main__' and '--lc' in sys.argv:
-    fx = make_lc()
-    path = os.path.join(ROOT, 'tests', 'golden', 'lc_r18_img64_b3.pt')
-    torch.save(fx, path)
-    print('lc fixture', fx['train_loss'], '%.1f KB' % (os.path.getsize(path) / 1e3))
+    for name, kw in (('lc_r18_img64_b3', dict()), ('lc_r50_img64_b2', dict(network='resnet50', B=2, seed_w=53, seed_x=54))):
+        if '--only' in sys.argv and name not in sys.argv:
+            continue
+        fx = make_lc(**kw)
+        path = os.path.join(ROOT, 'tests', 'golden', name + '.pt')
+        torch.save(fx, path)
+        print('lc fixture', name, fx['train_loss'], '%.1f KB' % (os.path.getsize(path) / 1e3))

@@ -49,6 +49,7 @@ def main():
     torch.cuda.synchronize()
     gathered = [torch.empty_like(tr.flat_p) for _ in range(world)]
     dist.all_gather(gathered, tr.flat_p)
+    g_dist = tr.flat_g.clone()                               # the all-reduced (summed) gradient
     init = [torch.empty_like(p0) for _ in range(world)]
     dist.all_gather(init, p0)
     res = None
@@ -69,7 +70,8 @@ def main():
         upd_d = (gathered[0] - p0).double()
         upd_s = (tr2.flat_p - p0).double()
         rel = float((upd_d - upd_s).norm() / upd_s.norm())
-        res = dict(world=world, same_init=bool(same_init), same_after=bool(same_after), update_rel_l2=rel,
+        grel = float((g_dist.double() - tr2.flat_g.double()).norm() / tr2.flat_g.double().norm())
+        res = dict(world=world, same_init=bool(same_init), same_after=bool(same_after), grad_rel_l2=grel, update_rel_l2=rel,
                    update_norm=float(upd_s.norm()), loss=float(loss))
         print('MPRESULT ' + json.dumps(res), flush=True)
     dist.barrier()

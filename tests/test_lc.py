@@ -15,8 +15,12 @@ def _block(fx):
     return torch.randn(fx['B'], 8, 3, 5, fx['img'], fx['img'], generator=g)
 
 
-def test_lc_oracle_matches_reference():
-    fx = load_fixture('lc_r18_img64_b3')
+LC_CASES = ['lc_r18_img64_b3', 'lc_r50_img64_b2']          # BasicBlock and Bottleneck (feature size 1024) backbones
+
+
+@pytest.mark.parametrize('case', LC_CASES)
+def test_lc_oracle_matches_reference(case):
+    fx = load_fixture(case)
     sd = O.lc_synthetic_state_dict(fx['network'], fx['seed_w'], fx['num_class'])
     assert list(sd.keys()) == fx['keys']
     block = _block(fx)
@@ -30,9 +34,10 @@ def test_lc_oracle_matches_reference():
 
 
 @pytest.mark.gpu
-def test_lc_cuda_matches_reference_and_oracle():
+@pytest.mark.parametrize('case', LC_CASES)
+def test_lc_cuda_matches_reference_and_oracle(case):
     from dpc_b200.model_3d_lc import LC
-    fx = load_fixture('lc_r18_img64_b3')
+    fx = load_fixture(case)
     sd = O.lc_synthetic_state_dict(fx['network'], fx['seed_w'], fx['num_class'])
     with contextlib.redirect_stdout(io.StringIO()):
         m = LC(fx['img'], 8, 5, network=fx['network'], dropout=0.0, num_class=fx['num_class'])
@@ -45,21 +50,23 @@ def test_lc_cuda_matches_reference_and_oracle():
     with torch.no_grad():
         out, ctxv = m(block)
     assert out.shape == fx['eval_output'].shape and ctxv.shape == fx['eval_context'].shape
-    assert rel_err(out, fx['eval_output'])[0] < 1e-3 and rel_err(ctxv, fx['eval_context'])[0] < 1e-3
+    # the 50-layer Bottleneck network at this tiny size is ~13x worse conditioned than r18 (tests/test_parity_gpu.py): 2e-3
+    tol = 2e-3 if 'r50' in case else 1e-3
+    assert rel_err(out, fx['eval_output'])[0] < tol and rel_err(ctxv, fx['eval_context'])[0] < tol
     m.train()
     out, ctxv = m(block)
-    assert rel_err(out, fx['train_output'])[0] < 1e-3 and rel_err(ctxv, fx['train_context'])[0] < 1e-3
+    assert rel_err(out, fx['train_output'])[0] < tol and rel_err(ctxv, fx['train_context'])[0] < tol
     B, nc = fx['B'], fx['num_class']
     loss = torch.nn.functional.cross_entropy(out.view(B, nc), (torch.arange(B) % nc).cuda())
-    assert abs(float(loss) - fx['train_loss']) < 1e-3 * max(1.0, fx['train_loss'])
+    assert abs(float(loss.detach()) - fx['train_loss']) < tol * max(1.0, fx['train_loss'])
     loss.backward()
     new = m.state_dict()
     for k, v in fx['new_stats'].items():                       # running statistics after one train-mode forward
-        assert rel_err(new[k], v)[0] < 1e-3, k
+        assert rel_err(new[k], v)[0] < tol, k
     assert int(new['final_bn.num_batches_tracked']) == fx['num_batches_tracked']
     for k, p in m.named_parameters():                          # gradients: chaotic at B = 3 (see test_parity_gpu.GRAD_TOL)
         assert p.grad is not None, k
-        check_sample_l2(p.grad, fx['grads'][k], 6e-2, k)
+        check_sample_l2(p.grad, fx['grads'][k], 0.3 if 'r50' in case else 6e-2, k)
 
 
 @pytest.mark.gpu

@@ -27,5 +27,8 @@ def test_nccl_data_parallel_step_matches_single_process(world):
     print(res)
     assert res['same_init'], 'FlatTrainer did not broadcast rank 0\'s parameters'
     assert res['same_after'], 'parameters differ across ranks after the step'
-    # the all-reduced step equals the single-process replay up to the summation order of the fp32 atomics
-    assert res['update_rel_l2'] < 2e-2, res
+    # the all-reduced gradient equals the single-process sum of the two shards' gradients up to the summation order of the
+    # atomics (amplified by the tiny-batch conditioning, profiles/r2_grad_table.md); the FIRST Adam step is lr * sign(g), so
+    # a near-zero gradient entry that changes sign moves the update by 2 lr: measured 3.9e-2 rel-L2 = 0.04 % of the entries
+    assert res['grad_rel_l2'] < 1e-2, res
+    assert res['update_rel_l2'] < 1e-1, res

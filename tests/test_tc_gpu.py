@@ -87,6 +87,25 @@ def test_gemm_nt_split(M, N, K, f16):
     assert rel(C2, ref + 1) < tol
 
 
+@pytest.mark.parametrize('M,N', [(128, 256), (6144, 6144), (1617, 1617), (6468, 6468), (200, 100), (36, 36)])
+@pytest.mark.parametrize('f16', [1, 0])
+def test_score_matmul(M, N, f16):
+    """persistent A-resident score matmul (score_tc.cu), K = 256: config-2 / config-4 / config-5 sizes, partial tiles, odd N"""
+    L = _lib()
+    K = 256
+    g = torch.Generator(device='cuda').manual_seed(5)
+    A = torch.randn(M, K, device='cuda', generator=g) * 0.25
+    B = torch.randn(N, K, device='cuda', generator=g)
+    ah, al = split(A, f16=bool(f16))
+    bh, bl = split(B, f16=bool(f16))
+    C = torch.full((M, N), float('nan'), device='cuda')
+    L.score_matmul_tc(M, N, K, ah.data_ptr(), al.data_ptr(), bh.data_ptr(), bl.data_ptr(), f16, C.data_ptr(), _st())
+    torch.cuda.synchronize()
+    assert not torch.isnan(C).any()
+    ref = A.double() @ B.double().t()
+    assert rel(C, ref) < (5e-6 if f16 else 5e-5)
+
+
 CASES = [
     # NB, T, H, W, Ci, Co, k, s, p
     (2, 5, 32, 32, 64, 64, (1, 3, 3), (1, 1, 1), (0, 1, 1)),
