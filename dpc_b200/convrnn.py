@@ -23,7 +23,21 @@ class ConvGRUCell(nn.Module):
             nn.init.constant_(gate.bias, 0.)
 
     def forward(self, input_tensor, hidden_state):
-        raise RuntimeError('ConvGRUCell is a parameter holder; the CUDA path runs inside DPC_RNN.forward')
+        """one GRU step (convrnn.py:24-34): input [B,C,H,W], hidden [B,C,H,W] or None -> new state [B,C,H,W].
+        (Inside DPC_RNN / LC the whole recurrence runs fused; this is the reference's stand-alone cell surface.)"""
+        if self.kernel_size != 1 or self.input_size != self.hidden_size or self.hidden_size % 64 != 0:
+            raise NotImplementedError('ConvGRUCell CUDA path: kernel_size=1, input=hidden (a multiple of 64) only')
+        if not input_tensor.is_cuda:
+            raise RuntimeError('dpc_b200 has no CPU path: input must be a CUDA tensor')
+        B, C, H, W = input_tensor.shape
+        rows = input_tensor.permute(0, 2, 3, 1).reshape(B * H * W, C).contiguous().float()
+        h0 = None if hidden_state is None else hidden_state.permute(0, 2, 3, 1).reshape(B * H * W, C).contiguous().float()
+        params = [self.reset_gate.weight, self.reset_gate.bias, self.update_gate.weight, self.update_gate.bias,
+                  self.out_gate.weight, self.out_gate.bias]
+        need = torch.is_grad_enabled() and (input_tensor.requires_grad or (h0 is not None and h0.requires_grad)
+                                            or any(q.requires_grad for q in params))
+        H_all = _GruSeqFn.apply(rows, h0, B * H * W, 1, 0.0, 0, need, *[q.contiguous() for q in params])
+        return H_all.view(B, H, W, C).permute(0, 3, 1, 2)
 
 
 class ConvGRU(nn.Module):

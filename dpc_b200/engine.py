@@ -285,9 +285,19 @@ def _bn_apply(y, mean, rstd, gamma, beta, relu, rows, C, st, res=None, res_plane
 
 @_timed('bn_bwd')
 def _bn_bwd(dout, out, relu, y, mean, rstd, gamma, rows, C, st, want_g=False, out_hi=None, want_rows=True,
-            want_planes=False, ws=None):
+            want_planes=False, ws=None, frozen=False):
     """-> (dy rows or None, dy planes or None, dgamma, dbeta, g or None).  ws: the reduction [sum g | sum g*xhat]
-    when the dgrad that produced `dout` already computed it in its epilogue (TcConvSite.dgrad_bnred)"""
+    when the dgrad that produced `dout` already computed it in its epilogue (TcConvSite.dgrad_bnred).
+    frozen: the BN normalised with FIXED statistics (eval mode of track_running_stats=True): dgamma / dbeta as usual,
+    but dy = gamma * rstd * g without the batch-statistics terms (a rarely used path: reduce, then an apply pass over
+    zeroed sums)"""
+    if frozen:
+        res = _bn_bwd(dout, out, relu, y, mean, rstd, gamma, rows, C, st, want_g=want_g, out_hi=out_hi, want_rows=want_rows,
+                      want_planes=want_planes)
+        zero = torch.zeros(2 * C, dtype=torch.float64, device=y.device)
+        dy, planes, _, _, g = _bn_bwd(dout, out, relu, y, mean, rstd, gamma, rows, C, st, want_g=want_g, out_hi=out_hi,
+                                      want_rows=want_rows, want_planes=want_planes, ws=zero)
+        return dy, planes, res[2], res[3], g
     fused = ws is not None
     if not fused:
         ws = torch.empty(2 * C, dtype=torch.float64, device=y.device)
@@ -393,8 +403,6 @@ def backbone_forward(network, x, P, need_ctx=True, bn_state=None, training=True)
     L = lib()
     st = _stream()
     running = bn_state is not None and not training
-    if running and need_ctx:
-        raise NotImplementedError('backward through eval-mode (running-statistics) BatchNorm is not built')
     NB, Cin, T, H, W = x.shape
     if Cin != 3:
         raise ValueError('backbone expects 3 input channels, got %d' % Cin)
@@ -429,10 +437,12 @@ def backbone_forward(network, x, P, need_ctx=True, bn_state=None, training=True)
         a0p = (torch.empty((rows_p, 64), **bf), torch.empty((rows_p, 64), **bf))
         _timed('stem_pool_fwd')(L.stem_pool_finalize)(ptr(ypool), ptr(idx), ptr(m0), ptr(r0), ptr(P['bn1.weight']), ptr(P['bn1.bias']),
                                                       ptr(a0p[0]), ptr(a0p[1]), None, rows_p, st)
-        ctx = dict(network=network, x=x, x2=x2, wp=wp, ypool=ypool, idx=idx, m0=m0, r0=r0, stem_dims=(NB, T, H, W, Ho, Wo), blocks=[])
+        ctx = dict(network=network, x=x, x2=x2, wp=wp, ypool=ypool, idx=idx, m0=m0, r0=r0, stem_dims=(NB, T, H, W, Ho, Wo), blocks=[],
+                   frozen=running)
         cur, cur_op = None, a0p
     else:
         cur, cur_op, ctx = _stem_forward_unpooled(L, st, x, P, bn_state, training, running, network)
+        ctx['frozen'] = running
     dims, C = (T, Hp, Wp), 64
     tc = USE_TC
     Site = TcConvSite if tc else ConvSite
@@ -622,7 +632,7 @@ def _backbone_backward(ctx, dout, P, side):
         relu = b['final_relu']
         has_ds = b['downsample']
         tc = rec['tc']
-        kw = dict(want_rows=not tc, want_planes=tc)          # conv-operand format of the dy tensors
+        kw = dict(want_rows=not tc, want_planes=tc, frozen=ctx.get('frozen', False))          # conv-operand format of the dy tensors
         op = (lambda rows, planes: planes) if tc else (lambda rows, planes: rows)
         if b['block'] == 'bottleneck':
             c3 = rec['c3']
@@ -719,6 +729,8 @@ def _backbone_backward(ctx, dout, P, side):
         G['bn1.weight'], G['bn1.bias'] = _empty((64,), ypool), _empty((64,), ypool)
         _timed('stem_tail_bwd')(L.stem_pool_bwd_reduce)(ptr(ypool), ptr(dout), ptr(ctx['idx']), ptr(ctx['m0']), ptr(ctx['r0']), ptr(ws),
                                                         ptr(G['bn1.weight']), ptr(G['bn1.bias']), rows_p, st)
+        if ctx.get('frozen'):
+            ws.zero_()                 # fixed (running) statistics: dy = gamma * rstd * g, no batch-statistics terms
         dw0 = torch.empty_like(P['conv1.weight'])
         if STEM_FUSE_WGRAD and L.stem_pool_supported(H, W) == 2:
             # conv1's wgrad MMAs run in the same kernel on the gradient tile in shared memory: no 5.4 GB gradient planes
@@ -734,6 +746,8 @@ def _backbone_backward(ctx, dout, P, side):
             del dout
             _timed('stem_wgrad')(L.stem_conv_wgrad_s2d)(ptr(x2[0]), ptr(x2[1]), ptr(dy0p[0]), ptr(dy0p[1]), ptr(dw0), NB, T, H, W, st)
     else:
+        if ctx.get('frozen'):
+            raise NotImplementedError('backward through eval-mode BatchNorm needs the pooled stem (even frame sizes)')
         dw0 = _stem_backward_unpooled(L, st, ctx, dout, P, G)
         del dout
     G['conv1.weight'] = dw0
@@ -1169,10 +1183,8 @@ def lc_head_forward(z4, dims, B, N, P, final_bn_state, training, gru_p, fc_p, se
     L.bias_relu(ptr(out), ptr(bias), ptr(out), 0, B, nc, st)
     ctx = None
     if need_ctx:
-        if not training:
-            raise NotImplementedError('backward through eval-mode (running-statistics) BatchNorm is not built')
         ctx = dict(B=B, N=N, S=S, D=D, To=To, R=R, z4=z4, X_all=X_all, steps=steps, vec=vec, mean=mean, rstd=rstd,
-                   keep=keep, cin=cin, nc=nc)
+                   keep=keep, cin=cin, nc=nc, frozen=not training)
     return out, context, ctx
 
 
@@ -1195,7 +1207,7 @@ def lc_head_backward(ctx, dout, dcontext, P):
     if dcontext is not None:
         L.scatter_rows(ptr(dcontext.contiguous()), ptr(dc), B, D, B, B, 0, 1, st)      # dc += dcontext
     dvec, _, G['final_bn.weight'], G['final_bn.bias'], _ = _bn_bwd(dc, None, False, ctx['vec'], ctx['mean'], ctx['rstd'],
-                                                                 P['final_bn.weight'], B, D, st)
+                                                                 P['final_bn.weight'], B, D, st, frozen=ctx.get('frozen', False))
     dh_last = _empty((R, D), dout)
     L.pool_split_bwd(ptr(ctx['vec']), ptr(dvec), None, ptr(dh_last), B, S, 1, D, st)
     dX_all, _ = gru_sequence_backward(ctx['steps'], ctx['X_all'], None, dh_last, P, R, N, G)

@@ -174,7 +174,7 @@ def make_lc(network='resnet18', img=64, B=3, seed_w=51, seed_x=52, num_class=101
 
 
 if __name__ == '__main__' and '--lc' in sys.argv:
-    for name, kw in (('lc_r18_img64_b3', dict()), ('lc_r50_img64_b2', dict(network='resnet50', B=2, seed_w=53, seed_x=54))):
+    for name, kw in (('lc_r18_img64_b3', dict()), ('lc_r50_img64_b4', dict(network='resnet50', B=4, seed_w=53, seed_x=54))):
         if '--only' in sys.argv and name not in sys.argv:
             continue
         fx = make_lc(**kw)
