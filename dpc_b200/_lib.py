@@ -23,11 +23,6 @@ _SIGS = {
     'dpc_abi_version': (c_int, []),
     'dpc_last_error': (c_char_p, []),
     'dpc_launch_count': (c_int64, []),
-    'dpc_pack_conv_weight': (c_int, [P, P, P, c_int, c_int, c_int, P]),
-    'dpc_unpack_conv_wgrad': (c_int, [P, P, c_int, c_int, c_int, P]),
-    'dpc_conv3d_fwd': (c_int, [POINTER(ConvGeom), P, P, P, P]),
-    'dpc_conv3d_dgrad': (c_int, [POINTER(ConvGeom), P, P, P, c_int, P]),
-    'dpc_conv3d_wgrad': (c_int, [POINTER(ConvGeom), P, P, P, P]),
     'dpc_split_bf16': (c_int, [P, P, P, c_int64, P]),
     'dpc_pack_conv_weight_bf16': (c_int, [P, P, P, P, P, c_int, c_int, c_int, P]),
     'dpc_score_matmul_tc': (c_int, [c_int, c_int, c_int, P, P, P, P, c_int, P, P]),
@@ -37,12 +32,9 @@ _SIGS = {
     'dpc_conv3d_dgrad_tc': (c_int, [POINTER(ConvGeom), P, P, P, P, P, c_int, P]),
     'dpc_conv3d_dgrad_bnred_tc': (c_int, [POINTER(ConvGeom), P, P, P, P, P, c_int, P, P, P, P, P, P]),
     'dpc_conv3d_wgrad_tc': (c_int, [POINTER(ConvGeom), P, P, P, P, P, P, P]),
-    'dpc_stem_conv_fwd': (c_int, [P, P, P, c_int, c_int, c_int, c_int, P]),
     'dpc_stem_conv_fwd_tc': (c_int, [P, P, P, P, c_int, c_int, c_int, c_int, P]),
     'dpc_stem_conv_wgrad_tc': (c_int, [P, P, P, P, c_int, c_int, c_int, c_int, P]),
-    'dpc_stem_conv_wgrad': (c_int, [P, P, P, c_int, c_int, c_int, c_int, P]),
     'dpc_stem_s2d_pack': (c_int, [P, P, P, c_int, c_int, c_int, c_int, P]),
-    'dpc_stem_conv_fwd_s2d': (c_int, [P, P, P, P, P, P, c_int, c_int, c_int, c_int, P]),
     'dpc_stem_conv_wgrad_s2d': (c_int, [P, P, P, P, P, c_int, c_int, c_int, c_int, P]),
     'dpc_stem_pool_supported': (c_int, [c_int, c_int]),
     'dpc_stem_s2d_wpack': (c_int, [P, P, P]),

@@ -6,34 +6,17 @@
 //   X2[h2,w2][(c,r,s)] = x[c, 2h2+r, 2w2+s],   W2[a,b][c,r,s] = w[c, 2a+r-1, 2b+s-1]  (0 where an index is -1)
 //
 // X2 is stored channels-last as split-bf16 planes with 16 channels per pixel (12 real + 4 zero): one pixel = one
-// 32-byte row = exactly one UMMA k-step (K = 16).  The forward kernel is then the halo-patch scheme of
-// conv_tc.cu: ONE TMA box (SWIZZLE_32B) brings the input patch of a 128-position tile, the 16 taps are 16
-// row-shifted K-major descriptors into it, the whole packed filter bank (16 taps x [W_hi ; W_lo] = 64 KB) is
-// resident in shared memory, and a tile costs 32 MMAs and ONE tcgen05.commit.  This replaces the CUDA-core
-// im2col build of stem_tc.cu (measured 7.8 ms at B = 128, issue-latency bound) by a TMA-fed kernel bounded by
-// the 5.4 GB output write.
+// 32-byte row = exactly one UMMA k-step (K = 16).  This file holds the shared pieces: the pack kernels (input planes,
+// filter bank) and the stand-alone wgrad kernel (used when the fused backward of stem_pool.cu does not fit shared memory);
+// the forward and the recomputing backward live in stem_pool.cu.
 //
-// Replaces nn.Conv3d(3, 64, (1,7,7), stride (1,2,2), padding (0,3,3)) at backbone/resnet_2d3d.py:134-135.
+// Replaces nn.Conv3d(3, 64, (1,7,7), stride (1,2,2), padding (0,3,3)) at backbone/resnet_2d3d.py:211.
 #include "tc_common.cuh"
 
 namespace {
 
 constexpr int S2D_CH = 16, S2D_TAPS = 16, S2D_BN = 64;
-constexpr int S2D_EC = 16;                                  // output columns per epilogue warp
-constexpr int S2D_NPB_MAX = 4;                              // patch buffers (and per-tile completion barriers) in flight
-constexpr int S2D_FWD_THREADS = 64 + 32 * 4 * (S2D_BN / S2D_EC);   // producer + MMA warp + epilogue warps
 constexpr uint32_t S2D_W_BYTES = S2D_TAPS * 2 * S2D_BN * 32;      // 64 KB: per tap [W_hi (64 rows) ; W_lo (64 rows)] x 32 B
-
-struct S2dMaps { CUtensorMap x_hi, x_lo, w; };
-
-struct S2dParams {
-    int PW, bhr;               // padded row pitch (Wo + 3) and rows per patch box
-    int Ho, Wo, T;
-    int tiles_per_frame, total_tiles;
-    int patch_bytes;           // one plane of the patch, rounded up to 1024
-    int npb;                   // patch buffers in flight (2 .. S2D_NPB_MAX, as shared memory allows)
-    int shift[S2D_TAPS];       // patch row shift per tap
-};
 
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
@@ -91,169 +74,6 @@ __global__ void stem_s2d_wpack_kernel(const float* __restrict__ w, __nv_bfloat16
 // K-major SWIZZLE_32B descriptors: rows of 32 bytes, 8-row atoms 256 bytes apart.  High word = SBO (256 >> 4) |
 // version 1 (bit 46) | layout type 6 (SWIZZLE_32B, bits 61-63); low word = start address >> 4 | LBO field (unused).
 constexpr uint64_t S2D_DHI = 0xC0004010ull << 32;
-
-__global__ void __launch_bounds__(S2D_FWD_THREADS, 1)
-stem_s2d_fwd_kernel(const __grid_constant__ S2dMaps maps, const S2dParams hp, float* __restrict__ y, double* __restrict__ stats) {
-    extern __shared__ __align__(1024) uint8_t smem_raw[];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    // smem: [filter bank 64 KB] [2 x (patch_hi | patch_lo)] [barriers] [BN partials]
-    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-    const uint32_t pbase = base + S2D_W_BYTES;
-    const uint32_t pbuf = 2u * (uint32_t)hp.patch_bytes;
-    const int NPB = hp.npb;
-    const uint32_t bar_base = pbase + (uint32_t)NPB * pbuf;
-    // p_full[b]: patch b landed;  tm_full[b] (b = tile % NPB): the tile's MMAs retired -- read by the epilogue
-    // (accumulator ready) AND by the producer (patch buffer b free again);  tm_empty[a] (a = tile & 1): TMEM buffer drained
-    auto p_full = [&](int b) { return bar_base + 8u * b; };
-    auto tm_full = [&](int b) { return bar_base + 8u * (S2D_NPB_MAX + b); };
-    auto tm_empty = [&](int b) { return bar_base + 8u * (2 * S2D_NPB_MAX + b); };
-    const uint32_t w_full = bar_base + 8u * (2 * S2D_NPB_MAX + 2), tmem_ptr_addr = w_full + 8u;
-    float* stat_smem = reinterpret_cast<float*>(smem_raw + (w_full + 16u - smem_u32(smem_raw)));
-    if (stats && threadIdx.x < 128) stat_smem[threadIdx.x] = 0.f;
-    const uint32_t tmem_cols = 4u * S2D_BN;
-    if (warp == 0 && lane == 0) {
-        asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.x_hi) : "memory");
-        asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.x_lo) : "memory");
-        asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.w) : "memory");
-        for (int b = 0; b < NPB; ++b) { mbar_init(p_full(b), 1); mbar_init(tm_full(b), 1); }
-        for (int b = 0; b < 2; ++b) mbar_init(tm_empty(b), 4 * (S2D_BN / S2D_EC));
-        mbar_init(w_full, 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    if (warp == 1) tmem_alloc(tmem_ptr_addr, tmem_cols);
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem_base = *reinterpret_cast<const uint32_t*>(smem_raw + (tmem_ptr_addr - smem_u32(smem_raw)));
-    const int my_tiles = ((int)blockIdx.x < hp.total_tiles) ? (hp.total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
-
-    // tile i of this CTA -> frame (n, t), first padded-pitch position f0, first output row of the tile
-    auto tile_origin = [&](int i, int& n, int& t, int& f0, int& hrow0) {
-        const int tile = (int)blockIdx.x + i * (int)gridDim.x;
-        const int frame = tile / hp.tiles_per_frame;
-        f0 = (tile - frame * hp.tiles_per_frame) * 128;
-        hrow0 = f0 / hp.PW;
-        n = frame / hp.T; t = frame - n * hp.T;
-    };
-
-    if (warp == 0) {
-        if (elect_one() && my_tiles > 0) {
-            mbar_expect_tx(w_full, S2D_W_BYTES);
-            for (int j = 0; j < 8; ++j) tma_load_2d(&maps.w, base + j * 8192, w_full, 0, j * 256);
-            const uint32_t patch_tx = 2u * (uint32_t)(hp.bhr * hp.PW) * 32u;
-            for (int i = 0; i < my_tiles; ++i) {
-                const int b = i % NPB;
-                if (i >= NPB) mbar_wait(tm_full(b), ((uint32_t)(i / NPB) - 1u) & 1u);   // tile i-NPB has retired: buffer free
-                int n, t, f0, hrow0;
-                tile_origin(i, n, t, f0, hrow0);
-                mbar_expect_tx(p_full(b), patch_tx);
-                tma_load_5d(&maps.x_hi, pbase + b * pbuf, p_full(b), 0, -2, hrow0 - 2, t, n);
-                tma_load_5d(&maps.x_lo, pbase + b * pbuf + hp.patch_bytes, p_full(b), 0, -2, hrow0 - 2, t, n);
-            }
-        }
-    } else if (warp == 1) {
-        if (elect_one() && my_tiles > 0) {
-            // D = f32, A = B = bf16, K-major, M = 128; N = 128 for X_hi x [W_hi ; W_lo], N = 64 for X_lo x W_hi
-            const uint32_t idesc_n = (1u << 4) | (1u << 7) | (1u << 10) | ((128u >> 4) << 24);
-            const uint32_t idesc2 = idesc_n | ((uint32_t)((2 * S2D_BN) >> 3) << 17);
-            const uint32_t idesc1 = idesc_n | ((uint32_t)(S2D_BN >> 3) << 17);
-            uint32_t sh2[S2D_TAPS];
-#pragma unroll
-            for (int t = 0; t < S2D_TAPS; ++t) sh2[t] = (uint32_t)hp.shift[t] * 2u;       // rows of 32 B in 16-byte units
-            const uint32_t patch16 = (uint32_t)hp.patch_bytes >> 4;
-            const uint32_t w_lo32 = (base >> 4) | 0x10000u;
-            mbar_wait(w_full, 0);
-            for (int i = 0; i < my_tiles; ++i) {
-                const int buf = i & 1;
-                const uint32_t td = tmem_base + (uint32_t)(buf * 2 * S2D_BN), tcx = td + (uint32_t)S2D_BN;
-                int n, t, f0, hrow0;
-                tile_origin(i, n, t, f0, hrow0);
-                const int pb = i % NPB;
-                const uint32_t a_lo32 = ((pbase + pb * pbuf + (uint32_t)(f0 - hrow0 * hp.PW) * 32u) >> 4) | 0x10000u;
-                mbar_wait(tm_empty(buf), (((uint32_t)i >> 1) & 1u) ^ 1u);
-                mbar_wait(p_full(pb), (uint32_t)(i / NPB) & 1u);
-                tc_fence_after();
-#pragma unroll
-                for (int tap = 0; tap < S2D_TAPS; ++tap) {
-                    const uint32_t ahi = a_lo32 + sh2[tap], alo = ahi + patch16, b = w_lo32 + (uint32_t)tap * (4096u >> 4);
-                    umma_bf16(td, S2D_DHI | (uint64_t)ahi, S2D_DHI | (uint64_t)b, idesc2, tap ? 1u : 0u);
-                    umma_bf16(tcx, S2D_DHI | (uint64_t)alo, S2D_DHI | (uint64_t)b, idesc1, 1u);
-                }
-                umma_commit(tm_full(pb));
-            }
-        }
-    } else {
-        // epilogue: 16 warps = 4 TMEM lane quarters (warp % 4) x four 16-column groups (the epilogue, not the MMAs,
-        // bounds this kernel: ncu showed the 8-warp version stalled on the TMEM loads with the tensor pipe 43 % active);
-        // BatchNorm partial sums stay in registers (one row per lane) across all tiles of the CTA and are transposed
-        // once at the end
-        const int q = warp & 3, c0 = ((warp - 2) >> 2) * S2D_EC;
-        float rs[S2D_EC], rq[S2D_EC];
-#pragma unroll
-        for (int j = 0; j < S2D_EC; ++j) { rs[j] = 0.f; rq[j] = 0.f; }
-        for (int i = 0; i < my_tiles; ++i) {
-            const int buf = i & 1;
-            const uint32_t td = tmem_base + (uint32_t)(buf * 2 * S2D_BN), tcx = td + (uint32_t)S2D_BN;
-            int n, t, f0, hrow0;
-            tile_origin(i, n, t, f0, hrow0);
-            const int f = f0 + q * 32 + lane;
-            const int h = f / hp.PW, w = f - h * hp.PW;
-            const bool valid = h < hp.Ho && w < hp.Wo;
-            const long long row = (((long long)n * hp.T + t) * hp.Ho + h) * hp.Wo + w;
-            mbar_wait(tm_full(i % NPB), (uint32_t)(i / NPB) & 1u);
-            tc_fence_after();
-            uint32_t v[S2D_EC], u[S2D_EC];
-            tmem_ld16_nowait(td + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
-            tmem_ld16_nowait(tcx + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, u);
-            tmem_ld_wait();
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(tm_empty(buf));
-            float4 o[S2D_EC / 4];
-#pragma unroll
-            for (int j = 0; j < S2D_EC / 4; ++j) {
-                o[j] = make_float4(__uint_as_float(v[4 * j]) + __uint_as_float(u[4 * j]),
-                                   __uint_as_float(v[4 * j + 1]) + __uint_as_float(u[4 * j + 1]),
-                                   __uint_as_float(v[4 * j + 2]) + __uint_as_float(u[4 * j + 2]),
-                                   __uint_as_float(v[4 * j + 3]) + __uint_as_float(u[4 * j + 3]));
-                if (stats && valid) {
-                    rs[4 * j] += o[j].x; rs[4 * j + 1] += o[j].y; rs[4 * j + 2] += o[j].z; rs[4 * j + 3] += o[j].w;
-                    rq[4 * j] += o[j].x * o[j].x; rq[4 * j + 1] += o[j].y * o[j].y;
-                    rq[4 * j + 2] += o[j].z * o[j].z; rq[4 * j + 3] += o[j].w * o[j].w;
-                }
-            }
-            // Stores: a lane pair (rows 2k, 2k+1) swaps halves of each 8-column group, so that one STG.128 of the pair
-            // fills a whole 32-byte sector of ONE row instead of two half sectors of two rows (ncu: the row-per-lane
-            // stores issued 2x the L2 write sectors and the L2 was 72 % busy).
-            pair_store_rows<S2D_EC / 8>(o, y, row, valid, lane, S2D_BN, c0, false);
-        }
-        if (stats) {
-            // transposing butterfly over the warp's 32 rows: after the halving steps lane l holds column c0 + (l >> 1)
-            // summed over 16 rows; the last exchange adds the other 16
-#pragma unroll
-            for (int off = 16, nn = S2D_EC / 2; nn >= 1; off >>= 1, nn >>= 1) {
-                const bool up = (lane & off) != 0;
-#pragma unroll
-                for (int i = 0; i < nn; ++i) {
-                    const float s_send = up ? rs[i] : rs[i + nn], s_keep = up ? rs[i + nn] : rs[i];
-                    const float q_send = up ? rq[i] : rq[i + nn], q_keep = up ? rq[i + nn] : rq[i];
-                    rs[i] = s_keep + __shfl_xor_sync(0xffffffffu, s_send, off);
-                    rq[i] = q_keep + __shfl_xor_sync(0xffffffffu, q_send, off);
-                }
-            }
-            rs[0] += __shfl_xor_sync(0xffffffffu, rs[0], 1);
-            rq[0] += __shfl_xor_sync(0xffffffffu, rq[0], 1);
-            if ((lane & 1) == 0) {
-                atomicAdd(&stat_smem[c0 + (lane >> 1)], rs[0]);
-                atomicAdd(&stat_smem[64 + c0 + (lane >> 1)], rq[0]);
-            }
-        }
-    }
-    tc_fence_before();
-    __syncthreads();
-    if (warp == 1) tmem_dealloc(tmem_base, tmem_cols);
-    if (stats && threadIdx.x < 128) atomicAdd(stats + threadIdx.x, (double)stat_smem[threadIdx.x]);
-}
 
 // =============================================================================================
 // wgrad of conv1 from the same planes:  dW2[co][(a,b)][ch] = sum_pos dY[pos, co] * X2[pos + (a-2, b-2)][ch]
@@ -427,62 +247,6 @@ extern "C" int dpc_stem_s2d_pack(const float* x, void* x2_hi, void* x2_lo, int N
 extern "C" int dpc_stem_s2d_wpack(const float* w, void* wp, void* stream) {
     DPC_REQUIRE(w && wp, "dpc_stem_s2d_wpack: bad args");
     stem_s2d_wpack_kernel<<<(S2D_TAPS * S2D_BN * S2D_CH + 255) / 256, 256, 0, as_stream(stream)>>>(w, reinterpret_cast<__nv_bfloat16*>(wp));
-    DPC_LAUNCH_CHECK();
-    return DPC_OK;
-}
-
-// y [NB,T,H/2,W/2,64] = conv1(x) from the space-to-depth planes; `wp`: scratch of 32768 bf16 for the packed filter
-// bank; bn_ws (nullable): 128 doubles = per-channel sum | sum of squares of y
-extern "C" int dpc_stem_conv_fwd_s2d(const void* x2_hi, const void* x2_lo, const float* w, void* wp, float* y, double* bn_ws,
-                                     int NB, int T, int H, int W, void* stream) {
-    DPC_REQUIRE(x2_hi && x2_lo && w && wp && y && NB > 0 && T > 0 && H > 0 && W > 0, "dpc_stem_conv_fwd_s2d: bad args");
-    DPC_REQUIRE((H & 1) == 0 && (W & 1) == 0, "dpc_stem_conv_fwd_s2d: H (%d) and W (%d) must be even", H, W);
-    cudaStream_t st = as_stream(stream);
-    const int Ho = H / 2, Wo = W / 2;
-    S2dParams hp;
-    memset(&hp, 0, sizeof(hp));
-    hp.PW = Wo + 3;
-    hp.bhr = 4 + (130 + hp.PW - 1) / hp.PW;                   // rows [rowoff, rowoff + 128 + 3 * PW + 3), rowoff < PW
-    DPC_REQUIRE(hp.PW <= 256 && hp.bhr <= 256, "dpc_stem_conv_fwd_s2d: frame too wide (%d)", W);
-    hp.Ho = Ho; hp.Wo = Wo; hp.T = T;
-    hp.tiles_per_frame = (Ho * hp.PW + 127) / 128;
-    const long long total = (long long)NB * T * hp.tiles_per_frame;
-    DPC_REQUIRE(total < (1ll << 31), "dpc_stem_conv_fwd_s2d: too many tiles");
-    hp.total_tiles = (int)total;
-    hp.patch_bytes = ((hp.bhr * hp.PW * 32 + 1023) / 1024) * 1024;
-    for (int a = 0; a < 4; ++a)
-        for (int b = 0; b < 4; ++b) hp.shift[a * 4 + b] = a * hp.PW + b;
-    hp.npb = S2D_NPB_MAX;
-    while (hp.npb > 2 && S2D_W_BYTES + 2 * hp.npb * (size_t)hp.patch_bytes + 128 + 512 + 1024 > 227 * 1024) --hp.npb;
-    const size_t smem = S2D_W_BYTES + 2 * hp.npb * (size_t)hp.patch_bytes + 128 + 512 + 1024;
-    DPC_REQUIRE(smem <= 227 * 1024, "dpc_stem_conv_fwd_s2d: patch does not fit shared memory (W = %d)", W);
-    auto enc = s2d_encode();
-    DPC_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled entry point not available");
-    stem_s2d_wpack_kernel<<<(S2D_TAPS * S2D_BN * S2D_CH + 255) / 256, 256, 0, st>>>(w, reinterpret_cast<__nv_bfloat16*>(wp));
-    DPC_LAUNCH_CHECK();
-    S2dMaps maps;
-    {
-        const cuuint64_t gd[5] = {S2D_CH, (cuuint64_t)Wo, (cuuint64_t)Ho, (cuuint64_t)T, (cuuint64_t)NB};
-        const cuuint64_t gs[4] = {32, (cuuint64_t)Wo * 32, (cuuint64_t)Ho * Wo * 32, (cuuint64_t)T * Ho * Wo * 32};
-        const cuuint32_t bx[5] = {S2D_CH, (cuuint32_t)hp.PW, (cuuint32_t)hp.bhr, 1, 1}, es[5] = {1, 1, 1, 1, 1};
-        for (int i = 0; i < 2; ++i) {
-            CUresult r = enc(i ? &maps.x_lo : &maps.x_hi, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(i ? x2_lo : x2_hi),
-                             gd, gs, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_32B,
-                             CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-            DPC_REQUIRE(r == CUDA_SUCCESS, "dpc_stem_conv_fwd_s2d: cuTensorMapEncodeTiled (x) failed (%d)", (int)r);
-        }
-        const cuuint64_t wd[2] = {S2D_CH, (cuuint64_t)S2D_TAPS * 2 * S2D_BN};
-        const cuuint64_t ws[1] = {32};
-        const cuuint32_t wb[2] = {S2D_CH, 256}, we[2] = {1, 1};
-        CUresult r = enc(&maps.w, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, wp, wd, ws, wb, we, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                         CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-        DPC_REQUIRE(r == CUDA_SUCCESS, "dpc_stem_conv_fwd_s2d: cuTensorMapEncodeTiled (w) failed (%d)", (int)r);
-    }
-    if (bn_ws) DPC_CUDA(cudaMemsetAsync(bn_ws, 0, sizeof(double) * 128, st));
-    DPC_CUDA(cudaFuncSetAttribute(stem_s2d_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const int sms = dpc_num_sms();
-    const int grid = hp.total_tiles < sms ? hp.total_tiles : sms;
-    stem_s2d_fwd_kernel<<<grid, S2D_FWD_THREADS, smem, st>>>(maps, hp, y, bn_ws);
     DPC_LAUNCH_CHECK();
     return DPC_OK;
 }

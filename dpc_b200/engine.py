@@ -94,8 +94,8 @@ def _out_extent(i, k, s, p):
 
 
 class ConvSite:
-    """geometry + packed weights of one Conv3d call site"""
-    __slots__ = ('geom', 'taps', 'Ci', 'Co', 'rows_in', 'rows_out', 'dims_out', 'wf', 'wd')
+    """geometry of one Conv3d call site"""
+    __slots__ = ('geom', 'taps', 'Ci', 'Co', 'rows_in', 'rows_out', 'dims_out')
 
     def __init__(self, NB, dims_in, Ci, Co, k, s, p):
         Ti, Hi, Wi = dims_in
@@ -108,59 +108,15 @@ class ConvSite:
         self.rows_in = NB * Ti * Hi * Wi
         self.rows_out = NB * To * Ho * Wo
         self.dims_out = (To, Ho, Wo)
-        self.wf = self.wd = None
-
-    def pack(self, w, st):
-        L = lib()
-        self.wf = _empty((self.taps, self.Ci, self.Co), w)
-        self.wd = _empty((self.taps, self.Co, self.Ci), w)
-        L.pack_conv_weight(ptr(w), ptr(self.wf), ptr(self.wd), self.Co, self.Ci, self.taps, st)
-
-    @_timed('conv_fwd')
-    def fwd(self, x, st):
-        y = _empty((self.rows_out, self.Co), x)
-        lib().conv3d_fwd(self.geom, ptr(x), ptr(self.wf), ptr(y), st)
-        return y
-
-    def fwd_bn(self, x, st):
-        """conv + BatchNorm batch statistics -> (y, mean, rstd)"""
-        y = self.fwd(x, st)
-        mean, rstd = _bn_stats(y, self.rows_out, self.Co, st)
-        return y, mean, rstd
-
-    @_timed('conv_dgrad')
-    def dgrad(self, dy, st, dx=None):
-        acc = 1
-        if dx is None:
-            dx = _empty((self.rows_in, self.Ci), dy)
-            acc = 0
-        lib().conv3d_dgrad(self.geom, ptr(dy), ptr(self.wd), ptr(dx), acc, st)
-        return dx
-
-    @_timed('conv_wgrad')
-    def wgrad(self, x, dy, st):
-        """returns dW in the parameter layout [Co,Ci,kT,kH,kW]"""
-        L = lib()
-        dwp = _empty((self.taps, self.Ci, self.Co), x)
-        L.conv3d_wgrad(self.geom, ptr(x), ptr(dy), ptr(dwp), st)
-        g = self.geom
-        dw = _empty((self.Co, self.Ci, g.kT, g.kH, g.kW), x)
-        L.unpack_conv_wgrad(ptr(dwp), ptr(dw), self.Co, self.Ci, self.taps, st)
-        return dw
 
 
-# tensor-core path switch: True = tcgen05 3xBF16-split kernels for every conv / the score matmul
-# (the default product path); False = exact-fp32 CUDA-core kernels (reference precision, used by
-# tests to cross-check the tensor-core path).
-USE_TC = True
 # BatchNorm-backward reductions in the epilogue of the stride-1 dgrads that produce their input (dgrad_bnred): False,
 # 'halo' (only the 64 -> 64 1x3x3 sites of layer1, whose halo-patch kernel prefetches the mask / y rows before it waits
 # for the accumulators) or True (every stride-1 site; measured slower on the tap-per-box kernels at B = 128: the per-row
 # gathers stall their 4-warp epilogue: layer2 +0.38 ms vs a 0.26 ms reduce pass, layer3 +0.31 vs 0.10).
 FUSE_BN_REDUCE = False
-# conv1 + bn1 + relu + maxpool without storing the conv1 output (stem_pool.cu); False = round-1 stem kernels
-STEM_POOL = True
-# ... and conv1's wgrad inside the recomputing backward kernel (the gradient on the conv1 grid is never stored either)
+# conv1's wgrad inside the recomputing stem backward kernel (stem_pool.cu); False = gradient planes to HBM + the separate
+# space-to-depth wgrad kernel (also the automatic fallback when the fused schedule does not fit shared memory)
 STEM_FUSE_WGRAD = True
 
 
@@ -352,48 +308,29 @@ def _conv_bn(site, op, name, bn_state, training, st):
 
 
 def _stem_forward_unpooled(L, st, x, P, bn_state, training, running, network):
-    """conv1 -> y0 (stored) -> bn1 + relu + maxpool: the exact-fp32 CUDA-core path (USE_TC = False), odd frame sizes
-    (stem_tc.cu) and frames the pooled-stem schedule does not cover.  Returns (a0 rows, conv operand, ctx)."""
+    """conv1 -> y0 (stored) -> bn1 + relu + maxpool for frames the pooled-stem schedule does not cover (odd H / W):
+    stem_tc.cu builds the im2col tile in shared memory.  Returns (a0 rows, conv operand planes, ctx)."""
     NB, Cin, T, H, W = x.shape
     Ho, Wo = _out_extent(H, 7, 2, 3), _out_extent(W, 7, 2, 3)
     rows0 = NB * T * Ho * Wo
     y0 = _empty((rows0, 64), x)
-    x2 = None
-    if USE_TC:
-        ws0 = None if running else torch.empty(128, dtype=torch.float64, device=x.device)
-        if H % 2 == 0 and W % 2 == 0:
-            # space-to-depth planes + TMA halo-patch kernel (stem_s2d.cu)
-            bf = dict(dtype=ACT, device=x.device)
-            x2 = (torch.empty((NB, T, H // 2, W // 2, 16), **bf), torch.empty((NB, T, H // 2, W // 2, 16), **bf))
-            wp = torch.empty(32768, **bf)
-            _timed('stem_fwd')(L.stem_s2d_pack)(ptr(x), ptr(x2[0]), ptr(x2[1]), NB, T, H, W, st)
-            _timed('stem_fwd')(L.stem_conv_fwd_s2d)(ptr(x2[0]), ptr(x2[1]), ptr(P['conv1.weight']), ptr(wp), ptr(y0), ptr(ws0),
-                                                    NB, T, H, W, st)
-            del wp
-        else:
-            x2 = None
-            _timed('stem_fwd')(L.stem_conv_fwd_tc)(ptr(x), ptr(P['conv1.weight']), ptr(y0), ptr(ws0), NB, T, H, W, st)
-        if not running:
-            m0, r0 = _empty((64,), x), _empty((64,), x)
-            L.bn_finalize(ptr(ws0), rows0, 64, BN_EPS, ptr(m0), ptr(r0), st)
-    else:
-        _timed('stem_fwd')(L.stem_conv_fwd)(ptr(x), ptr(P['conv1.weight']), ptr(y0), NB, T, H, W, st)
-        if not running:
-            m0, r0 = _bn_stats(y0, rows0, 64, st)
+    ws0 = None if running else torch.empty(128, dtype=torch.float64, device=x.device)
+    _timed('stem_fwd')(L.stem_conv_fwd_tc)(ptr(x), ptr(P['conv1.weight']), ptr(y0), ptr(ws0), NB, T, H, W, st)
     if running:
         m0 = bn_state['bn1'][0]
         r0 = torch.empty_like(m0)
         L.bn_rstd_from_var(ptr(bn_state['bn1'][1]), BN_EPS, ptr(r0), 64, st)
-    elif bn_state is not None:
-        L.bn_running_update(ptr(m0), ptr(r0), rows0, BN_EPS, BN_MOMENTUM, ptr(bn_state['bn1'][0]), ptr(bn_state['bn1'][1]), 64, st)
+    else:
+        m0, r0 = _empty((64,), x), _empty((64,), x)
+        L.bn_finalize(ptr(ws0), rows0, 64, BN_EPS, ptr(m0), ptr(r0), st)
+        if bn_state is not None:
+            L.bn_running_update(ptr(m0), ptr(r0), rows0, BN_EPS, BN_MOMENTUM, ptr(bn_state['bn1'][0]), ptr(bn_state['bn1'][1]), 64, st)
     Hp, Wp = _out_extent(Ho, 3, 2, 1), _out_extent(Wo, 3, 2, 1)
     a0 = _empty((NB * T * Hp * Wp, 64), x)
     _timed('stem_pool_fwd')(L.bn_relu_maxpool_fwd)(ptr(y0), ptr(m0), ptr(r0), ptr(P['bn1.weight']), ptr(P['bn1.bias']), ptr(a0),
-                          NB * T, Ho, Wo, 64, st)
-    ctx = dict(network=network, x=x, x2=x2, y0=y0, m0=m0, r0=r0, a0=a0, stem_dims=(NB, T, H, W, Ho, Wo), blocks=[])
-    cur = a0
-    cur_op = _split(cur, st) if USE_TC else cur
-    return cur, cur_op, ctx
+                                                   NB * T, Ho, Wo, 64, st)
+    ctx = dict(network=network, x=x, y0=y0, m0=m0, r0=r0, a0=a0, stem_dims=(NB, T, H, W, Ho, Wo), blocks=[])
+    return a0, _split(a0, st), ctx
 
 
 def backbone_forward(network, x, P, need_ctx=True, bn_state=None, training=True):
@@ -412,7 +349,7 @@ def backbone_forward(network, x, P, need_ctx=True, bn_state=None, training=True)
     Hp, Wp = _out_extent(Ho, 3, 2, 1), _out_extent(Wo, 3, 2, 1)
     rows_p = NB * T * Hp * Wp
     bf = dict(dtype=ACT, device=x.device)
-    pooled = USE_TC and STEM_POOL and L.stem_pool_supported(H, W) >= 1
+    pooled = L.stem_pool_supported(H, W) >= 1
     if pooled:
         # conv1 + bn1 + relu + maxpool with the conv1 output never stored (stem_pool.cu): the kernel keeps, per pooled
         # position, the conv value the pool selects (+ its window index) and bn1's batch sums over all conv positions
@@ -444,8 +381,8 @@ def backbone_forward(network, x, P, need_ctx=True, bn_state=None, training=True)
         cur, cur_op, ctx = _stem_forward_unpooled(L, st, x, P, bn_state, training, running, network)
         ctx['frozen'] = running
     dims, C = (T, Hp, Wp), 64
-    tc = USE_TC
-    Site = TcConvSite if tc else ConvSite
+    tc = True                      # conv operands are always split-bf16 planes (tcgen05 kernels)
+    Site = TcConvSite
     spec = backbone_spec(network)
     for bi, b in enumerate(spec):
         p = b['name']
@@ -592,28 +529,17 @@ def backbone_backward(ctx, dout, P):
 def _stem_backward_unpooled(L, st, ctx, dout, P, G):
     """backward of _stem_forward_unpooled; fills G['bn1.*'] and returns dW of conv1"""
     NB, T, H, W, Ho, Wo = ctx['stem_dims']
-    rows0 = NB * T * Ho * Wo
-    # max-pool bwd + ReLU bwd + bn1 bwd fused: the 5.4 GB (B=128) gradient on the conv1 grid is never stored
-    tc = USE_TC
+    # max-pool bwd + ReLU bwd + bn1 bwd fused (two passes, no materialised pooling gradient)
     y0 = ctx['y0']
-    dy0 = None if tc else torch.empty_like(y0)
-    dy0p = (torch.empty(y0.shape, dtype=GRD, device=y0.device),
-            torch.empty(y0.shape, dtype=GRD, device=y0.device)) if tc else (None, None)
+    dy0p = (torch.empty(y0.shape, dtype=GRD, device=y0.device), torch.empty(y0.shape, dtype=GRD, device=y0.device))
     ws = torch.empty(128, dtype=torch.float64, device=y0.device)
     G['bn1.weight'], G['bn1.bias'] = _empty((64,), y0), _empty((64,), y0)
     _timed('stem_tail_bwd')(L.stem_tail_bwd)(ptr(y0), ptr(ctx['m0']), ptr(ctx['r0']), ptr(P['bn1.weight']),
                                              ptr(P['bn1.bias']), ptr(ctx['a0']), ptr(dout), ptr(ws),
-                                             ptr(G['bn1.weight']), ptr(G['bn1.bias']), ptr(dy0), ptr(dy0p[0]),
+                                             ptr(G['bn1.weight']), ptr(G['bn1.bias']), None, ptr(dy0p[0]),
                                              ptr(dy0p[1]), NB * T, Ho, Wo, 64, 1, st)
-    del dout
     dw0 = torch.empty_like(P['conv1.weight'])
-    if tc and ctx.get('x2') is not None:
-        x2 = ctx['x2']
-        _timed('stem_wgrad')(L.stem_conv_wgrad_s2d)(ptr(x2[0]), ptr(x2[1]), ptr(dy0p[0]), ptr(dy0p[1]), ptr(dw0), NB, T, H, W, st)
-    elif tc:
-        _timed('stem_wgrad')(L.stem_conv_wgrad_tc)(ptr(ctx['x']), ptr(dy0p[0]), ptr(dy0p[1]), ptr(dw0), NB, T, H, W, st)
-    else:
-        _timed('stem_wgrad')(L.stem_conv_wgrad)(ptr(ctx['x']), ptr(dy0), ptr(dw0), NB, T, H, W, st)
+    _timed('stem_wgrad')(L.stem_conv_wgrad_tc)(ptr(ctx['x']), ptr(dy0p[0]), ptr(dy0p[1]), ptr(dw0), NB, T, H, W, st)
     return dw0
 
 
@@ -843,7 +769,7 @@ HEAD_CHAIN = True
 
 
 def _head_chain_ok(D):
-    return HEAD_CHAIN and USE_TC and D == 256
+    return HEAD_CHAIN and D == 256
 
 
 def _head_forward_chain(z4, dims, B, N, pred_step, P, dropout_p, seed, need_ctx):
@@ -1003,11 +929,8 @@ def head_forward(z4, dims, B, N, pred_step, P, dropout_p=0.0, seed=0, need_ctx=T
     finf_rows = _empty((M, D), z4)
     L.gather_rows(ptr(finf_all), ptr(finf_rows), M, D, pred_step * S, N * S, Tagg * S, st)
     score = _empty((M, M), z4)
-    if USE_TC:
-        pp, fp = _split(pred_rows, st, f16=True), _split(finf_rows, st, f16=True)
-        _timed('score_fwd')(L.gemm_nt_split_tc)(M, M, D, ptr(pp[0]), ptr(pp[1]), ptr(fp[0]), ptr(fp[1]), 1, ptr(score), 0, st)
-    else:
-        _gemm(0, 1, M, M, D, pred_rows, D, finf_rows, D, score, M, st)
+    pp, fp = _split(pred_rows, st, f16=True), _split(finf_rows, st, f16=True)
+    _timed('score_fwd')(L.gemm_nt_split_tc)(M, M, D, ptr(pp[0]), ptr(pp[1]), ptr(fp[0]), ptr(fp[1]), 1, ptr(score), 0, st)
     ctx = None
     if need_ctx:
         ctx = dict(B=B, N=N, P=pred_step, S=S, D=D, To=To, R=R, M=M, finf_all=finf_all, X_all=X_all,
@@ -1033,7 +956,7 @@ def head_backward(ctx, dscore, P):
     W0, W2 = P['network_pred.0.weight'], P['network_pred.2.weight']
     dpred_rows = _empty((M, D), dscore)
     dfinf_rows = _empty((M, D), dscore)
-    if USE_TC and M % 64 == 0:
+    if M % 64 == 0:
         dsp = _split(dscore, st)
         # dpred = dS . finf      -> NT GEMM against finf^T (tiny transpose: data movement only)
         ftp = _split(ctx['finf_rows'].t().contiguous(), st)

@@ -39,25 +39,11 @@ const char* dpc_last_error(void);
 /* number of kernel launches issued by this library in this process (bench.py's gpu_launches) */
 int64_t dpc_launch_count(void);
 
-/* ---- Conv3d 1x3x3 / 3x3x3 / 1x1x1, bias-free --------------------------------------------
- * replaces nn.Conv3d forward/backward at backbone/resnet_2d3d.py:13-31 (conv3x3x3, conv1x3x3),
- * :241-244 (downsample 1x1x1) as used by BasicBlock2d/3d.forward (:64-80, :100-116).
- * Weights are consumed in packed form (see dpc_pack_conv_weight). Ci % 16 == 0, Co % 64 == 0. */
-int dpc_pack_conv_weight(const float* w /*[Co,Ci,kT,kH,kW]*/, float* wf /*[taps,Ci,Co]*/,
-                         float* wd /*[taps,Co,Ci]*/, int Co, int Ci, int taps, void* stream);
-int dpc_unpack_conv_wgrad(const float* dwp /*[taps,Ci,Co]*/, float* dw /*[Co,Ci,taps]*/,
-                          int Co, int Ci, int taps, void* stream);
-int dpc_conv3d_fwd(const dpc_conv_geom* g, const float* x, const float* wf, float* y, void* stream);
-/* dx = dgrad (accumulate == 0) or dx += dgrad (accumulate != 0) */
-int dpc_conv3d_dgrad(const dpc_conv_geom* g, const float* dy, const float* wd, float* dx,
-                     int accumulate, void* stream);
-/* dwp [taps,Ci,Co] is overwritten */
-int dpc_conv3d_wgrad(const dpc_conv_geom* g, const float* x, const float* dy, float* dwp, void* stream);
-
 /* ---- tcgen05 tensor-core path (3xBF16 split: fp32-equivalent to ~1e-5) ----------------------
  * Operands are pairs of bf16 planes: hi = bf16(x), lo = bf16(x - hi), multiplied as hi*hi + hi*lo + lo*hi into fp32 TMEM
- * accumulators.  Same call sites as above (conv3x3x3 / conv1x3x3 / 1x1x1 at resnet_2d3d.py:13-31,241-244) plus
- * torch.matmul at dpc/model_3d.py:83.  Channel counts must be multiples of 64.  tcgen05 kind::f16 needs ONE input format per
+ * accumulators.  Replaces nn.Conv3d forward / backward at backbone/resnet_2d3d.py:13-31 (conv3x3x3, conv1x3x3), :241-244
+ * (downsample 1x1x1) as used by BasicBlock2d/3d.forward (:64-80, :100-116) and Bottleneck2d/3d.forward, plus torch.matmul at
+ * dpc/model_3d.py:83.  Channel counts must be multiples of 64.  tcgen05 kind::f16 needs ONE input format per
  * instruction, and wgrad multiplies activations by gradients (which need bf16's exponent range), so activations are bf16
  * pairs too; a GEMM whose operands are both forward values may use fp16 pairs (dpc_split_f16, ~22 mantissa bits). */
 int dpc_split_bf16(const float* src, void* hi, void* lo, int64_t n, void* stream);
@@ -93,16 +79,8 @@ int dpc_conv3d_wgrad_tc(const dpc_conv_geom* g, const void* x_hi, const void* x_
                         const void* dy_lo, float* dwp, float* dw, void* stream);
 
 /* ---- stem: Conv3d(3,64,(1,7,7),s(1,2,2),p(0,3,3)) reading the caller's NCDHW input ----------
- * replaces backbone/resnet_2d3d.py:211,260 (self.conv1).  x [NB,3,T,H,W] -> y [NB,T,H/2,W/2,64]. */
-int dpc_stem_conv_fwd(const float* x, const float* w /*[64,3,1,7,7]*/, float* y,
-                      int NB, int T, int H, int W, void* stream);
-/* same, with conv1's weight gradient dw [64,3,1,7,7] computed by the same kernel (needs dpc_stem_pool_supported(H, W) == 2) */
-int dpc_stem_pool_bwd_wgrad(const void* x2_hi, const void* x2_lo, const void* wp, const float* dout, const void* idx,
-                            const float* mean, const float* rstd, const float* gamma, const double* ws, float* dw,
-                            int NB, int T, int H, int W, void* stream);
-int dpc_stem_conv_wgrad(const float* x, const float* dy, float* dw /*[64,3,1,7,7]*/,
-                        int NB, int T, int H, int W, void* stream);
-/* tcgen05 versions (3xBF16 split; the im2col tile is built in shared memory from the fp32 video).
+ * replaces backbone/resnet_2d3d.py:211,260 (self.conv1).  x [NB,3,T,H,W] -> y [NB,T,H/2,W/2,64].
+ * Fallback for odd frame sizes (3xBF16 split on tcgen05; the im2col tile is built in shared memory from the fp32 video).
  * bn_ws (nullable, 128 doubles) receives the per-channel sum | sum of squares of y (bn1 statistics). */
 int dpc_stem_conv_fwd_tc(const float* x, const float* w, float* y, double* bn_ws, int NB, int T, int H, int W,
                          void* stream);
@@ -111,11 +89,8 @@ int dpc_stem_conv_wgrad_tc(const float* x, const void* dy_hi, const void* dy_lo,
                            int H, int W, void* stream);
 /* Space-to-depth formulation of conv1 (same reference site): the stride-2 7x7 conv is a stride-1 4x4 conv over
  * X2[h2,w2][(c,r,s)] = x[c,2*h2+r,2*w2+s], stored as split-bf16 planes [NB,T,H/2,W/2,16] (12 real channels).
- * dpc_stem_s2d_pack builds the planes (H, W even); dpc_stem_conv_fwd_s2d computes y [NB,T,H/2,W/2,64] (+ bn1
- * statistics in bn_ws, nullable) with TMA-fed tcgen05 MMAs; `wp` = scratch of 32768 bf16 for the packed filters. */
+ * dpc_stem_s2d_pack builds the planes (H, W even). */
 int dpc_stem_s2d_pack(const float* x, void* x2_hi, void* x2_lo, int NB, int T, int H, int W, void* stream);
-int dpc_stem_conv_fwd_s2d(const void* x2_hi, const void* x2_lo, const float* w, void* wp, float* y, double* bn_ws,
-                          int NB, int T, int H, int W, void* stream);
 /* dw [64,3,1,7,7] from the space-to-depth planes and the split-bf16 planes of dy [NB,T,H/2,W/2,64] */
 int dpc_stem_conv_wgrad_s2d(const void* x2_hi, const void* x2_lo, const void* dy_hi, const void* dy_lo, float* dw,
                             int NB, int T, int H, int W, void* stream);
@@ -137,6 +112,10 @@ int dpc_stem_pool_bwd_reduce(const float* ypool, const float* dout, const void* 
 int dpc_stem_pool_bwd(const void* x2_hi, const void* x2_lo, const void* wp, const float* dout, const void* idx,
                       const float* mean, const float* rstd, const float* gamma, const double* ws, void* dy_hi, void* dy_lo,
                       int NB, int T, int H, int W, void* stream);
+/* same, with conv1's weight gradient dw [64,3,1,7,7] computed by the same kernel (needs dpc_stem_pool_supported(H, W) == 2) */
+int dpc_stem_pool_bwd_wgrad(const void* x2_hi, const void* x2_lo, const void* wp, const float* dout, const void* idx,
+                            const float* mean, const float* rstd, const float* gamma, const double* ws, float* dw,
+                            int NB, int T, int H, int W, void* stream);
 
 /* ---- BatchNorm3d(track_running_stats=False): batch statistics always ----------------------
  * replaces nn.BatchNorm3d at resnet_2d3d.py:55,59,91,95,212,243 (+ relu_ / `out += residual`

@@ -43,10 +43,10 @@ def test_bad_arguments_return_error_codes_not_crashes():
     with pytest.raises(DpcLibError, match='bad dims'):
         L.gemm_f32(0, 0, 0, 4, 4, 1.0, None, 4, None, 4, 0.0, None, 4, None)
     g = ConvGeom(1, 1, 4, 4, 3, 1, 4, 4, 64, 1, 3, 3, 1, 1, 1, 0, 1, 1)       # Ci = 3: unsupported
-    with pytest.raises(DpcLibError, match='multiples of 16'):
-        L.conv3d_fwd(g, 1, 1, 1, None)
+    with pytest.raises(DpcLibError, match='multiples of 64'):
+        L.conv3d_fwd_tc(g, 1, 1, 1, 1, 1, None, None)
     g = ConvGeom(1, 1, 4, 4, 64, 1, 5, 4, 64, 1, 3, 3, 1, 1, 1, 0, 1, 1)       # wrong Ho
     with pytest.raises(DpcLibError, match='output extent'):
-        L.conv3d_fwd(g, 1, 1, 1, None)
+        L.conv3d_fwd_tc(g, 1, 1, 1, 1, 1, None, None)
     with pytest.raises(DpcLibError, match='unsupported channel count'):
         L.bn_stats(1, 10, 6, 1, 1, 1, 1e-5, None)

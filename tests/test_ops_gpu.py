@@ -38,49 +38,6 @@ def from_rows(r, NB, T, H, W):
     return r.view(NB, T, H, W, -1).permute(0, 4, 1, 2, 3).contiguous()
 
 
-CONV_CASES = [
-    # NB, T, H, W, Ci, Co, k, s, p
-    (3, 5, 16, 16, 64, 64, (1, 3, 3), (1, 1, 1), (0, 1, 1)),
-    (2, 5, 16, 16, 64, 128, (1, 3, 3), (1, 2, 2), (0, 1, 1)),
-    (2, 5, 16, 16, 64, 128, (1, 1, 1), (1, 2, 2), (0, 0, 0)),
-    (3, 5, 8, 8, 128, 256, (3, 3, 3), (2, 2, 2), (1, 1, 1)),
-    (3, 5, 8, 8, 128, 256, (1, 1, 1), (2, 2, 2), (0, 0, 0)),
-    (3, 3, 4, 4, 256, 256, (3, 3, 3), (1, 1, 1), (1, 1, 1)),
-    (5, 3, 7, 7, 256, 256, (3, 3, 3), (2, 2, 2), (1, 1, 1)),       # odd extents (224^2 path)
-    (1, 2, 2, 2, 256, 256, (3, 3, 3), (1, 1, 1), (1, 1, 1)),       # smaller than one tile
-]
-
-
-@pytest.mark.parametrize('case', CONV_CASES)
-def test_conv3d_fwd_dgrad_wgrad(case):
-    from dpc_b200.engine import ConvSite
-    NB, T, H, W, Ci, Co, k, s, p = case
-    g = torch.Generator(device='cuda').manual_seed(1)
-    x = torch.randn(NB, Ci, T, H, W, device='cuda', generator=g)
-    w = torch.randn(Co, Ci, *k, device='cuda', generator=g) / math.sqrt(Ci * k[0] * k[1] * k[2])
-    site = ConvSite(NB, (T, H, W), Ci, Co, k, s, p)
-    site.pack(w, _st())
-    xr = to_rows(x)
-    y = site.fwd(xr, _st())
-    xref = x.clone().requires_grad_(True)
-    wref = w.clone().requires_grad_(True)
-    yref = F.conv3d(xref, wref, None, s, p)
-    To, Ho, Wo = site.dims_out
-    assert tuple(yref.shape[2:]) == (To, Ho, Wo)
-    assert rel(from_rows(y, NB, To, Ho, Wo), yref) < 2e-5
-    dy = torch.randn(yref.shape, device='cuda', generator=g)
-    yref.backward(dy)
-    dyr = to_rows(dy)
-    dx = site.dgrad(dyr, _st())
-    assert rel(from_rows(dx, NB, T, H, W), xref.grad) < 2e-5
-    base = torch.randn_like(xr)
-    dx2 = site.dgrad(dyr, _st(), dx=base.clone())
-    assert rel(dx2 - base, to_rows(xref.grad)) < 5e-5
-    dw = site.wgrad(xr, dyr, _st())
-    assert dw.shape == w.shape
-    assert rel(dw, wref.grad) < 5e-5
-
-
 @pytest.mark.parametrize('NB,T,H,W', [(2, 5, 64, 64), (3, 2, 32, 48), (1, 1, 28, 20), (1, 2, 27, 21)])
 def test_stem_conv(NB, T, H, W):
     L = _lib()
@@ -88,14 +45,11 @@ def test_stem_conv(NB, T, H, W):
     x = torch.randn(NB, 3, T, H, W, device='cuda', generator=g)
     w = torch.randn(64, 3, 1, 7, 7, device='cuda', generator=g) * 0.1
     Ho, Wo = (H - 1) // 2 + 1, (W - 1) // 2 + 1
-    y = torch.empty(NB * T * Ho * Wo, 64, device='cuda')
-    L.stem_conv_fwd(x.data_ptr(), w.data_ptr(), y.data_ptr(), NB, T, H, W, _st())
     xr, wr = x.clone(), w.clone().requires_grad_(True)
     yref = F.conv3d(xr, wr, None, (1, 2, 2), (0, 3, 3))
     assert tuple(yref.shape[2:]) == (T, Ho, Wo)
-    assert rel(from_rows(y, NB, T, Ho, Wo), yref) < 2e-5
-    # tensor-core version + fused bn1 statistics
-    y2 = torch.full_like(y, float('nan'))
+    # conv1 from the fp32 video (odd-frame fallback) + fused bn1 statistics
+    y2 = torch.full((NB * T * Ho * Wo, 64), float('nan'), device='cuda')
     ws = torch.empty(128, dtype=torch.float64, device='cuda')
     L.stem_conv_fwd_tc(x.data_ptr(), w.data_ptr(), y2.data_ptr(), ws.data_ptr(), NB, T, H, W, _st())
     torch.cuda.synchronize()
@@ -106,29 +60,15 @@ def test_stem_conv(NB, T, H, W):
     assert float((mean - y2.double().mean(0)).abs().max()) < 1e-5 * float(y2.abs().max())
     assert rel(rstd, 1 / torch.sqrt(y2.double().var(0, unbiased=False) + 1e-5)) < 1e-5
     if H % 2 == 0 and W % 2 == 0:
-        # space-to-depth + TMA halo-patch version
+        # space-to-depth planes (the conv over them is covered by test_stem_pool)
         bf = dict(dtype=torch.bfloat16, device='cuda')
         x2h, x2l = torch.empty(NB, T, H // 2, W // 2, 16, **bf), torch.empty(NB, T, H // 2, W // 2, 16, **bf)
         L.stem_s2d_pack(x.data_ptr(), x2h.data_ptr(), x2l.data_ptr(), NB, T, H, W, _st())
         xs = x.view(NB, 3, T, H // 2, 2, W // 2, 2).permute(0, 2, 3, 5, 1, 4, 6).reshape(NB, T, H // 2, W // 2, 12)
         assert torch.equal(x2h[..., :12], xs.to(torch.bfloat16)) and not x2h[..., 12:].any()
         assert float(((x2h.float() + x2l.float())[..., :12] - xs).abs().max()) < 2.0 ** -15 * float(xs.abs().max())
-        y3 = torch.full_like(y, float('nan'))
-        ws3 = torch.empty(128, dtype=torch.float64, device='cuda')
-        wp = torch.empty(32768, **bf)
-        L.stem_conv_fwd_s2d(x2h.data_ptr(), x2l.data_ptr(), w.data_ptr(), wp.data_ptr(), y3.data_ptr(), ws3.data_ptr(),
-                            NB, T, H, W, _st())
-        torch.cuda.synchronize()
-        assert not torch.isnan(y3).any()
-        assert rel(from_rows(y3, NB, T, Ho, Wo), yref) < 5e-5
-        L.bn_finalize(ws3.data_ptr(), y3.shape[0], 64, 1e-5, mean.data_ptr(), rstd.data_ptr(), _st())
-        assert float((mean - y3.double().mean(0)).abs().max()) < 1e-5 * float(y3.abs().max())
-        assert rel(rstd, 1 / torch.sqrt(y3.double().var(0, unbiased=False) + 1e-5)) < 1e-5
     dy = torch.randn(yref.shape, device='cuda', generator=g)
     yref.backward(dy)
-    dw = torch.empty_like(w)
-    L.stem_conv_wgrad(x.data_ptr(), to_rows(dy).data_ptr(), dw.data_ptr(), NB, T, H, W, _st())
-    assert rel(dw, wr.grad) < 5e-5
     from dpc_b200 import engine as E
     dyp = E._split(to_rows(dy), _st())
     dw2 = torch.full_like(w, float('nan'))

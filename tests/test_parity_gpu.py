@@ -95,44 +95,40 @@ def test_grads_vs_golden(case):
     print('worst sampled grad rel err', worst)
 
 
-@pytest.mark.parametrize('use_tc', [False, True])
-def test_bottleneck_network_grads_vs_oracle(use_tc):
-    """resnet50 (Bottleneck2d/3d, feature size 1024): loss and every parameter gradient against the fp32 oracle.
-    This tiny case is very ill-conditioned: the fp32 oracle's own gradients are 1.1e-2 (worst tensor) / 8.6e-3 (all
-    parameters) from an fp64 run.  The exact-fp32 CUDA-core path (engine.USE_TC = False) checks the block wiring at
-    that noise floor (GOLDEN_GRAD_TOL); the 3xBF16 tensor-core path amplifies the same chaos ~8x (measured 9e-2 /
-    7e-2, as r18: 1.4e-2 vs 1.5e-3) and gets the loss at TOL plus a bound that only catches wiring errors."""
+def test_bottleneck_network_grads_vs_oracle():
+    """resnet50 (Bottleneck2d/3d, feature size 1024): loss against the fp32 oracle, every parameter gradient against an
+    fp64 run of the oracle, calibrated by the fp32 oracle's own distance from fp64.  This tiny case (B=2, BatchNorm over
+    a handful of rows in layer4) is very ill-conditioned: the fp32 oracle is already ~1e-2 from fp64.  The 3xBF16 path
+    (unit roundoff ~2^-16 per product vs 2^-24) measured ~8x that noise here, as on r18 (1.4e-2 vs 1.5e-3); the bound is
+    12x the measured fp32 noise, per tensor and over all parameters - a wiring error gives O(1).  The conv sites of the
+    Bottleneck blocks are pinned individually against fp64 convolutions in test_tc_gpu.py."""
     from oracle import dpc_oracle as O
-    from dpc_b200 import engine
     fx = load_fixture('r50_img64_b2')
     sd = O.synthetic_state_dict(fx['network'], fx['seed_w'])
     block = make_block(fx)
     import dpc_b200
-    old = engine.USE_TC
-    engine.USE_TC = use_tc
-    try:
-        m = build(fx['network'], fx['img'], fx['pred_step'], sd).eval()
-        loss = dpc_b200.NCECriterion()(m(block.cuda())[0])
-        loss.backward()
-        torch.cuda.synchronize()
-    finally:
-        engine.USE_TC = old
-    ref_loss, _, ref_grads = O.train_step_grads(block, sd, fx['network'], fx['pred_step'])
-    assert abs(float(loss) - float(ref_loss)) < (2e-3 if use_tc else 1e-4) * max(1.0, abs(float(ref_loss)))
-    num = den = 0.0
-    worst = 0.0
+    m = build(fx['network'], fx['img'], fx['pred_step'], sd).eval()
+    loss = dpc_b200.NCECriterion()(m(block.cuda())[0])
+    loss.backward()
+    torch.cuda.synchronize()
+    ref_loss, _, g32 = O.train_step_grads(block, sd, fx['network'], fx['pred_step'])
+    _, _, g64 = O.train_step_grads(block.double(), {k: v.double() for k, v in sd.items()}, fx['network'], fx['pred_step'])
+    assert abs(float(loss) - float(ref_loss)) < 2e-3 * max(1.0, abs(float(ref_loss)))
+    num = nnum = den = 0.0
+    worst = nworst = 0.0
     for k, p in m.named_parameters():
         assert p.grad is not None and torch.isfinite(p.grad).all(), k
-        d = (p.grad.cpu() - ref_grads[k]).double()
-        worst = max(worst, float(d.norm() / ref_grads[k].double().norm().clamp_min(1e-30)))
+        ref = g64[k]
+        d = p.grad.cpu().double() - ref
+        dn = g32[k].double() - ref
+        worst = max(worst, float(d.norm() / ref.norm().clamp_min(1e-30)))
+        nworst = max(nworst, float(dn.norm() / ref.norm().clamp_min(1e-30)))
         num += float(d.pow(2).sum())
-        den += float(ref_grads[k].double().pow(2).sum())
-    allp = (num / den) ** 0.5
-    print('r50 grads (tensor cores %s): worst tensor rel-L2 %.3e, all parameters %.3e' % (use_tc, worst, allp))
-    if use_tc:
-        assert allp < 0.2 and worst < 0.3
-    else:
-        assert allp < GOLDEN_GRAD_TOL and worst < 2 * GOLDEN_GRAD_TOL
+        nnum += float(dn.pow(2).sum())
+        den += float(ref.pow(2).sum())
+    allp, nall = (num / den) ** 0.5, (nnum / den) ** 0.5
+    print('r50 grads vs fp64: ours worst tensor %.3e all %.3e; fp32 oracle worst %.3e all %.3e' % (worst, allp, nworst, nall))
+    assert allp <= 12 * nall and worst <= 12 * nworst
 
 
 def test_grads_calibrated_against_fp64():
