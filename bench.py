@@ -66,9 +66,9 @@ def _out_dims(img, seq_len=5):
 
 
 def ncu_evidence():
-    """per-kernel numbers of the committed `ncu --set full` captures (profiles/r1_ncu_summary.json): DRAM traffic per
+    """per-kernel numbers of the committed `ncu --set full` captures (profiles/r2_ncu_summary.json): DRAM traffic per
     launch vs algorithmic bytes, tensor-pipe activity -- static evidence, not re-measured by this run"""
-    p = os.path.join(ROOT, 'profiles', 'r1_ncu_summary.json')
+    p = os.path.join(ROOT, 'profiles', 'r2_ncu_summary.json')
     if not os.path.exists(p):
         return None
     keep = ('kernel', 'site', 'ncu_duration_ms', 'dram_bytes', 'traffic_over_algorithmic', 'tensor_pipe_active_pct',
