@@ -31,9 +31,9 @@ timeout 200 $N -k regex:stem_pool_bwd_kernel  -s 1  -c 1 -o gpurun_out/${TAG}_st
 timeout 200 $N -k regex:bn_bwd_apply          -s 15 -c 1 -o gpurun_out/${TAG}_bn_bwd     $P > /dev/null 2>&1   # layer1 site
 timeout 200 $N -k regex:head_chain_fwd        -s 1  -c 1 -o gpurun_out/${TAG}_head_fwd   $P > /dev/null 2>&1
 timeout 200 $N -k regex:head_chain_bwd        -s 1  -c 1 -o gpurun_out/${TAG}_head_bwd   $P > /dev/null 2>&1
-# score matmul + NCE (second iteration of profile_score.py): conv_tc_kernel launches per iteration: fwd, dpred
-timeout 200 $N -k regex:conv_tc_kernel        -s 2  -c 1 -o gpurun_out/${TAG}_score_fwd  $S > /dev/null 2>&1
-timeout 200 $N -k regex:conv_tc_kernel        -s 3  -c 1 -o gpurun_out/${TAG}_score_dpred $S > /dev/null 2>&1
+# score matmul + NCE (second iteration of profile_score.py)
+timeout 200 $N -k regex:score_gemm_kernel     -s 1  -c 1 -o gpurun_out/${TAG}_score_fwd  $S > /dev/null 2>&1
+timeout 200 $N -k regex:conv_tc_kernel        -s 1  -c 1 -o gpurun_out/${TAG}_score_dpred $S > /dev/null 2>&1
 timeout 200 $N -k regex:wgrad_tc_kernel       -s 1  -c 1 -o gpurun_out/${TAG}_score_dfinf $S > /dev/null 2>&1
 timeout 200 $N -k regex:ce_fwd                -s 1  -c 1 -o gpurun_out/${TAG}_ce_fwd     $S > /dev/null 2>&1
 timeout 200 $N -k regex:ce_bwd                -s 1  -c 1 -o gpurun_out/${TAG}_ce_bwd     $S > /dev/null 2>&1

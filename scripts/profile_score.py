@@ -1,5 +1,5 @@
 """the score matmul + NCE criterion alone at BASELINE config 2 / 5 sizes (M = B*P*SQ rows, D = 256), for ncu captures:
-   ncu ... python scripts/profile_score.py [M]      launches: split x2, conv_tc_kernel (score fwd), ce_fwd, ce_bwd,
+   ncu ... python scripts/profile_score.py [M]      launches: split x2, score_gemm_kernel (score fwd), ce_fwd, ce_bwd,
    split (dscore), conv_tc_kernel (dpred), wgrad_tc_kernel (dfinf)"""
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -17,7 +17,7 @@ finf = torch.randn(M, D, device='cuda', generator=g)
 for _ in range(2):
     pp, fp = E._split(pred, st, f16=True), E._split(finf, st, f16=True)
     score = torch.empty(M, M, device='cuda')
-    L.gemm_nt_split_tc(M, M, D, ptr(pp[0]), ptr(pp[1]), ptr(fp[0]), ptr(fp[1]), 1, ptr(score), 0, st)
+    L.score_matmul_tc(M, M, D, ptr(pp[0]), ptr(pp[1]), ptr(fp[0]), ptr(fp[1]), 1, ptr(score), st)
     out, lse = E.nce_ce_forward(score)
     d = E.nce_ce_backward(score, lse, torch.ones(1, device='cuda'))
     dsp = E._split(d, st)
