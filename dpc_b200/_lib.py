@@ -75,6 +75,7 @@ _SIGS = {
     'dpc_relu_pool_bwd': (c_int, [P, P, P, c_int, c_int, c_int64, P]),
     'dpc_dropout_fwd': (c_int, [P, P, P, c_float, c_uint64, c_uint64, c_int64, P]),
     'dpc_mul': (c_int, [P, P, P, c_int64, P]),
+    'dpc_augment_clips': (c_int, [P, P, P, P, P, P] + [c_int] * 9 + [P]),
     'dpc_adam_step': (c_int, [P, P, P, P, c_int64, c_float, c_float, c_float, c_float, c_float, c_int, c_float, P]),
 }
 

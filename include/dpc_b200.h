@@ -263,6 +263,18 @@ int dpc_mul(const float* a, const float* b, float* out, int64_t n, void* stream)
 int dpc_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1,
                   float beta2, float eps, float wd, int step, float gscale, void* stream);
 
+/* ---- on-device clip augmentation (augment.cu): decoded uint8 frames -> the float32 block DPC_RNN.forward consumes --------
+ * replaces the CPU transform chain utils/augmentation.py:147-384 composed as dpc/main.py:115-133 (RandomSizedCrop | RandomCrop +
+ * Scale, RandomHorizontalFlip, RandomGray, ColorJitter, ToTensor, Normalize) and the reshuffle of dpc/dataset_3d.py:108-112,
+ * bit-exact with Pillow / torchvision arithmetic.  frames [B,F,H,W,3] uint8 (device); out [B,num_seq,3,seq_len,Ho,Wo] float32.
+ * tables (device, int32), per clip (Wo + Ho) * (2 + K) + 1 values: xstart[Wo] xcount[Wo] xcoef[Wo][K] ystart[Ho] ycount[Ho]
+ *   ycoef[Ho][K] xstep -- separable resampling taps in SOURCE coordinates, 22-bit fixed point (crop, flips, resize folded in);
+ * frame_params (device, int32), per frame 10 values: grey channel (-1 none), op[4] (0 brightness 1 contrast 2 saturation 3 hue,
+ *   -1 end), factor[4] (float32 bits), hue byte.  mean / stdv: 3 floats each, HOST pointers. */
+int dpc_augment_clips(const uint8_t* frames, const int32_t* tables, const int32_t* frame_params, const float* mean,
+                      const float* stdv, float* out, int B, int F, int H, int W, int Ho, int Wo, int K, int num_seq,
+                      int seq_len, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
