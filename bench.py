@@ -39,6 +39,7 @@ def parse():
     ap.add_argument('--no_cpu_baseline', action='store_true')
     ap.add_argument('--no_e2e', action='store_true')
     ap.add_argument('--no_stock', action='store_true', help='skip the stock PyTorch-CUDA leg')
+    ap.add_argument('--no_pipeline', action='store_true', help='skip the on-device input pipeline leg')
     ap.add_argument('--stock_steps', type=int, default=4)
     return ap.parse_args()
 
@@ -379,6 +380,75 @@ def run_b200(a, rank, local_rank, world):
                'h2d_bytes_per_step': host[0].numel() * 4, 'd2h_bytes_per_step': 4,
                'ms_per_step': ms_e2e, 'wall_ms_per_step': wall / a.steps}
 
+    # ---- on-device input pipeline: decoded uint8 frames -> H2D -> augment kernel -> step ----------
+    # the reference's CPU transform chain (utils/augmentation.py, main.py:125-133) replaced by dpc_b200.augmentation; the
+    # random decisions of batch i+1 are drawn on the host while the GPU runs step i
+    pipe = None
+    if not a.no_pipeline and not a.no_e2e:
+        import random as _random
+        import numpy as _np
+        from dpc_b200 import augmentation as aug
+        fw, fh = (200, 150) if a.img_dim <= 128 else (340, 256)      # k400-style frames: short side 150 (256 for 224^2)
+        tr = aug.k400_transform(a.img_dim)
+        _random.seed(1234 + rank)
+        _np.random.seed(1234 + rank)
+        hostf = [torch.randint(0, 256, (B, 40, fh, fw, 3), dtype=torch.uint8).pin_memory() for _ in range(2)]
+        fbufs = [torch.empty((B, 40, fh, fw, 3), dtype=torch.uint8, device=dev) for _ in range(2)]
+        blk = bufs[0]                                                # reuse the e2e leg's block buffer
+        fready = [torch.cuda.Event() for _ in range(2)]
+        ffree = [torch.cuda.Event() for _ in range(2)]
+
+        def fprefetch(i):
+            j = i % 2
+            with torch.cuda.stream(copy_stream):
+                copy_stream.wait_event(ffree[j])
+                fbufs[j].copy_(hostf[j], non_blocking=True)
+                fready[j].record(copy_stream)
+
+        for j in range(2):
+            ffree[j].record()
+        t_plan = time.perf_counter()
+        plans = [tr.plan(40, fw, fh) for _ in range(B)]
+        t_plan = (time.perf_counter() - t_plan) * 1e3
+        _tb, _fp, _, _ = tr.pack(plans)
+        side_bytes = int(_tb.nbytes + _fp.nbytes)                    # resampling tables + per-frame decisions, uploaded per batch
+        fprefetch(0)
+        torch.cuda.current_stream().wait_event(fready[0])
+        ka, kb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        tr(fbufs[0], 8, 5, plans=plans, out=blk)                     # warm-up
+        ka.record()
+        for _ in range(5):
+            tr(fbufs[0], 8, 5, plans=plans, out=blk)
+        kb.record()
+        ffree[0].record()
+        barrier()
+        aug_ms = ka.elapsed_time(kb) / 5
+        fprefetch(0)
+        pv0, pv1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        for i in range(1 + a.steps):
+            if i == 1:
+                barrier()
+                pv0.record()
+            fprefetch(i + 1)
+            torch.cuda.current_stream().wait_event(fready[i % 2])
+            tr(fbufs[i % 2], 8, 5, plans=plans, out=blk)
+            ffree[i % 2].record()
+            loss = step(blk)
+            plans = [tr.plan(40, fw, fh) for _ in range(B)]          # next batch's draws, under the running step
+            _ = loss.item()
+        pv1.record()
+        barrier()
+        ms_p = max_over_ranks(pv0.elapsed_time(pv1)) / a.steps
+        pipe = {'frames': 'uint8 [%d, 40, %d, %d, 3] per GPU (decoded RGB, synthetic)' % (B, fh, fw),
+                'recipe': 'k400 (main.py:125-133): RandomSizedCrop, RandomHorizontalFlip, RandomGray, ColorJitter, ToTensor, Normalize',
+                'augment_ms_per_batch': aug_ms, 'augment_clips_s': B / (aug_ms / 1e3),
+                'augment_gbs': (hostf[0].numel() + blk.numel() * 4) / (aug_ms / 1e3) / 1e9,
+                'host_draw_ms_per_batch': t_plan,
+                'e2e_uint8': {'value': world * B / (ms_p / 1e3), 'unit': 'clips/s', 'ms_per_step': ms_p,
+                              'h2d_bytes_per_step': hostf[0].numel() + side_bytes,
+                              'd2h_bytes_per_step': 4}}
+        del hostf, fbufs
+
     # ---- roofline of the dominant kernel family (one extra, instrumented step) -------------------
     roof = None
     fam = None
@@ -471,6 +541,7 @@ def run_b200(a, rank, local_rank, world):
                 'clocks': clocks, 'e2e': e2e, 'gpu_launches': int(launches), 'roofline': roof,
                 'cpu_baseline': cpu, 'kernel_families_ms': fam, 'loss': last_loss,
                 'allreduce_ms': allreduce_ms, 'rank_ms_per_step': rank_ms, 'conv_sites_ms': sites,
+                'input_pipeline': pipe,
                 'stock_cuda': stock,
                 'vs_stock_cuda': (value / stock['clips_s']) if stock and stock.get('clips_s') else None,
                 'vs_stock_cuda_ideal_ddp': (value / stock['ideal_ddp_clips_s']) if stock and stock.get('ideal_ddp_clips_s') else None}

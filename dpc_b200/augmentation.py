@@ -20,6 +20,7 @@ Supported: the two recipes of main.py (k400: RandomSizedCrop incl. its Scale + C
 RandomCrop(224) -> Scale((d, d)) NEAREST), RandomGray(consistent=False), ColorJitter(consistent=False), geometric steps
 `consistent=True`.  Anything else raises NotImplementedError -- there is no CPU fallback.
 """
+import functools
 import math
 import random
 
@@ -238,6 +239,7 @@ class Normalize:
 # ---------------------------------------------------------------------------------------------------------------
 # resampling tables (Pillow's Resample.c coefficients, in double precision exactly as the C code computes them)
 # ---------------------------------------------------------------------------------------------------------------
+@functools.lru_cache(maxsize=4096)
 def _bilinear_table(n_in, n_out):
     scale = n_in / n_out
     fscale = scale if scale > 1.0 else 1.0
@@ -260,6 +262,7 @@ def _bilinear_table(n_in, n_out):
     return lo.astype(np.int32), cnt.astype(np.int32), coef.astype(np.int32)
 
 
+@functools.lru_cache(maxsize=256)
 def _nearest_table(n_in, n_out):
     scale = n_in / n_out
     xo = scale * 0.5
@@ -270,6 +273,7 @@ def _nearest_table(n_in, n_out):
     return idx, np.ones(n_out, np.int32), np.full((n_out, 1), 1 << _PREC, np.int32)
 
 
+@functools.lru_cache(maxsize=256)
 def _identity_table(n):
     return np.arange(n, dtype=np.int32), np.ones(n, np.int32), np.full((n, 1), 1 << _PREC, np.int32)
 

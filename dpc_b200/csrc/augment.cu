@@ -46,7 +46,9 @@ __device__ __forceinline__ int blend8(int a, int b, float alpha, bool interp) {
 __device__ __forceinline__ int luma(int r, int g, int b) { return (r * 19595 + g * 38470 + b * 7471 + 0x8000) >> 16; }
 
 // convert("HSV"), hue byte += shift (mod 256), convert("RGB") -- Convert.c rgb2hsv_row / hsv2rgb
-__device__ __forceinline__ void hue_rotate(int& r, int& g, int& b, int shift) {
+// `lut_i` / `lut_f` / `lut_fs`: per byte, floor(h * 6 / 255), its float remainder and (float)(s / 255) of hsv2rgb
+__device__ __forceinline__ void hue_rotate(int& r, int& g, int& b, int shift, const int* lut_i, const float* lut_f,
+                                           const float* lut_fs) {
     const int maxc = max(r, max(g, b)), minc = min(r, min(g, b));
     int uh = 0, us = 0;
     if (minc != maxc) {
@@ -65,10 +67,9 @@ __device__ __forceinline__ void hue_rotate(int& r, int& g, int& b, int shift) {
     uh = (uh + shift) & 255;
     const int v = maxc;
     if (us == 0) { r = g = b = v; return; }
-    const double hf = __ddiv_rn(__dmul_rn((double)uh, 6.0), 255.0);
-    const int i = (int)floor(hf);
-    const double f = (double)(float)__dsub_rn(hf, (double)i);
-    const double fs = (double)(float)__ddiv_rn((double)us, 255.0);
+    const int i = lut_i[uh];
+    const double f = (double)lut_f[uh];
+    const double fs = (double)lut_fs[us];
     const double vf = (double)v;
     // C round() of a non-negative value == floor(x + 0.5) here
     const int p = clip8((int)floor(__dadd_rn(__dmul_rn(vf, __dsub_rn(1.0, fs)), 0.5)));
@@ -89,6 +90,20 @@ augment_kernel(const AugParams p) {
     extern __shared__ uint8_t img[];                // [3][Ho * Wo]
     __shared__ unsigned long long red[AUG_THREADS / 32];
     __shared__ int s_mean;
+    __shared__ int lut_i[256];
+    __shared__ float lut_f[256], lut_fs[256], lut_out[3][256];
+    if (threadIdx.x < 256) {
+        const int u = threadIdx.x;
+        const double hf = __ddiv_rn(__dmul_rn((double)u, 6.0), 255.0);
+        const int i = (int)floor(hf);
+        lut_i[u] = i;
+        lut_f[u] = (float)__dsub_rn(hf, (double)i);
+        lut_fs[u] = (float)__ddiv_rn((double)u, 255.0);
+#pragma unroll
+        for (int c = 0; c < 3; ++c)                     // ToTensor + Normalize of a byte, IEEE float32
+            lut_out[c][u] = __fdiv_rn(__fsub_rn(__fdiv_rn((float)u, 255.f), p.mean[c]), p.stdv[c]);
+    }
+    __syncthreads();
     const int f = blockIdx.x % p.F, b = blockIdx.x / p.F;
     const int npix = p.Ho * p.Wo;
     const int tab_len = (p.Wo + p.Ho) * (2 + p.K) + 1;
@@ -154,21 +169,28 @@ augment_kernel(const AugParams p) {
                 const int L = luma(r, g, bl);
                 r = blend8(L, r, alpha, interp); g = blend8(L, g, alpha, interp); bl = blend8(L, bl, alpha, interp);
             } else {
-                hue_rotate(r, g, bl, shift);
+                hue_rotate(r, g, bl, shift, lut_i, lut_f, lut_fs);
             }
             pr[i] = (uint8_t)r; pg[i] = (uint8_t)g; pb[i] = (uint8_t)bl;
         }
         __syncthreads();                                 // s_mean / red are reused by a later contrast step
     }
-    // 3. ToTensor (/255) + Normalize ((x - mean) / std), IEEE float32; block[b, n, c, t, :, :]
+    // 3. ToTensor (/255) + Normalize ((x - mean) / std) through the per-byte table; block[b, n, c, t, :, :]
+    __syncthreads();                                     // the vector loads below cross the per-thread pixel ownership
     const int n = f / p.SL, t = f - n * p.SL;
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
         float* dst = p.out + ((((size_t)b * p.N + n) * 3 + c) * p.SL + t) * npix;
         const uint8_t* pl = img + c * npix;
-        const float m = p.mean[c], s = p.stdv[c];
-        for (int i = threadIdx.x; i < npix; i += AUG_THREADS)
-            dst[i] = __fdiv_rn(__fsub_rn(__fdiv_rn((float)pl[i], 255.f), m), s);
+        const float* lut = lut_out[c];
+        if ((npix & 3) == 0) {
+            for (int i = threadIdx.x; i < (npix >> 2); i += AUG_THREADS) {
+                const uchar4 v = reinterpret_cast<const uchar4*>(pl)[i];
+                reinterpret_cast<float4*>(dst)[i] = make_float4(lut[v.x], lut[v.y], lut[v.z], lut[v.w]);
+            }
+        } else {
+            for (int i = threadIdx.x; i < npix; i += AUG_THREADS) dst[i] = lut[pl[i]];
+        }
     }
 }
 

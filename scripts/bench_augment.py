@@ -31,6 +31,23 @@ for i in range(12):
         ts.append(a.elapsed_time(b))
 ts.sort()
 med = ts[len(ts) // 2]
+# the kernel alone (tables already on the device)
+from dpc_b200._lib import lib, ptr
+tables, fpar, (Wo, Ho), K = packed
+t_d, f_d = torch.from_numpy(tables).cuda(), torch.from_numpy(fpar).cuda()
+mean, std = np.asarray(plans[0].normalize[0], np.float32), np.asarray(plans[0].normalize[1], np.float32)
+ks = []
+for i in range(12):
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    lib().augment_clips(ptr(frames), ptr(t_d), ptr(f_d), mean.ctypes.data, std.ctypes.data, ptr(out), B, N * SL, H, W, Ho, Wo, K,
+                        N, SL, torch.cuda.current_stream().cuda_stream)
+    b.record()
+    torch.cuda.synchronize()
+    if i >= 2:
+        ks.append(a.elapsed_time(b))
+ks.sort()
+print('kernel alone: median %.3f ms (%.1f GB/s), K = %d taps' % (ks[len(ks) // 2], (frames.numel() + out.numel() * 4) / ks[len(ks) // 2] / 1e6, K))
 gb = (frames.numel() + out.numel() * 4) / 1e9
 print('augment B=%d %dx%d -> %d^2: kernel+upload median %.3f ms (%.1f GB/s of frames in + block out, %.0f clips/s); '
       'host: draw %.1f ms, tables %.1f ms per batch' % (B, W, H, S, med, gb / med * 1e3, B / med * 1e3, (t1 - t0) * 1e3,
