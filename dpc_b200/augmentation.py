@@ -346,7 +346,19 @@ class Compose:
             fpar[b, :, 9] = P.hue
         return tables, fpar, (Wo, Ho), K
 
-    def __call__(self, frames, num_seq, seq_len, plans=None, out=None):
+    def prepare(self, plans, device):
+        """pack the plans of one batch and start their upload (pinned staging, asynchronous on the current stream); the
+        result can be handed to __call__ later -- e.g. prepared under the previous training step"""
+        tables, fpar, (Wo, Ho), K = self.pack(plans)
+        with torch.cuda.device(device):
+            t_d = torch.from_numpy(tables).pin_memory().to(device, non_blocking=True)
+            f_d = torch.from_numpy(fpar).pin_memory().to(device, non_blocking=True)
+        mean = np.asarray(plans[0].normalize[0], np.float32)
+        std = np.asarray(plans[0].normalize[1], np.float32)
+        return dict(tables=t_d, frame_params=f_d, size=(Wo, Ho), K=K, mean=mean, std=std, B=len(plans), F=plans[0].n_frames,
+                    src=(plans[0].W, plans[0].H))
+
+    def __call__(self, frames, num_seq, seq_len, plans=None, out=None, prepared=None):
         """frames: CUDA uint8 [B, F, H, W, 3] (or [F, H, W, 3]) decoded RGB frames, F = num_seq * seq_len
         -> float32 block [B, num_seq, 3, seq_len, Ho, Wo] (dataset_3d.py:108-112 layout, batched)"""
         if frames.dtype != torch.uint8 or frames.dim() not in (4, 5) or frames.shape[-1] != 3:
@@ -359,19 +371,22 @@ class Compose:
         B, F, H, W, _ = frames.shape
         if F != num_seq * seq_len:
             raise ValueError('num_seq * seq_len = %d but the clips have %d frames' % (num_seq * seq_len, F))
-        if plans is None:
-            plans = [self.plan(F, W, H) for _ in range(B)]
-        tables, fpar, (Wo, Ho), K = self.pack(plans)
-        dev = frames.device
-        with torch.cuda.device(dev):
-            t_d = torch.from_numpy(tables).pin_memory().to(dev, non_blocking=True)
-            f_d = torch.from_numpy(fpar).pin_memory().to(dev, non_blocking=True)
+        if prepared is None:
+            if plans is None:
+                plans = [self.plan(F, W, H) for _ in range(B)]
+            prepared = self.prepare(plans, frames.device)
+        if (prepared['B'], prepared['F'], prepared['src']) != (B, F, (W, H)):
+            raise ValueError('the prepared batch is for %s clips x %s frames of %s, the frames are %s'
+                             % (prepared['B'], prepared['F'], prepared['src'], tuple(frames.shape)))
+        Wo, Ho = prepared['size']
+        with torch.cuda.device(frames.device):
             if out is None:
-                out = torch.empty(B, num_seq, 3, seq_len, Ho, Wo, device=dev)
-            mean = np.asarray(plans[0].normalize[0], np.float32)
-            std = np.asarray(plans[0].normalize[1], np.float32)
-            lib().augment_clips(ptr(frames), ptr(t_d), ptr(f_d), mean.ctypes.data, std.ctypes.data, ptr(out), B, F, H, W, Ho, Wo,
-                                K, num_seq, seq_len, torch.cuda.current_stream().cuda_stream)
+                out = torch.empty(B, num_seq, 3, seq_len, Ho, Wo, device=frames.device)
+            elif tuple(out.shape) != (B, num_seq, 3, seq_len, Ho, Wo) or out.dtype != torch.float32 or not out.is_contiguous():
+                raise ValueError('out must be a contiguous float32 [%d, %d, 3, %d, %d, %d]' % (B, num_seq, seq_len, Ho, Wo))
+            lib().augment_clips(ptr(frames), ptr(prepared['tables']), ptr(prepared['frame_params']),
+                                prepared['mean'].ctypes.data, prepared['std'].ctypes.data, ptr(out), B, F, H, W, Ho, Wo,
+                                prepared['K'], num_seq, seq_len, torch.cuda.current_stream().cuda_stream)
         return out
 
 
