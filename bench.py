@@ -318,7 +318,8 @@ def run_b200(a, rank, local_rank, world):
     for _ in range(a.warmup):
         step(x_dev)
     barrier()
-    sampler = ClockSampler(local_rank) if rank == 0 else None
+    sampler = ClockSampler(local_rank)                                # every rank samples its own GPU
+    trainer.allreduce_events = [] if world > 1 else None
     n0 = L.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -328,14 +329,21 @@ def run_b200(a, rank, local_rank, world):
     barrier()
     ms_local = e0.elapsed_time(e1)
     ms_total = max_over_ranks(ms_local)
-    rank_ms = None
-    if world > 1:                                                    # every rank's own device time per step
-        t = torch.tensor([ms_local / a.steps], device=dev, dtype=torch.float64)
-        allt = [torch.zeros_like(t) for _ in range(world)]
-        dist.all_gather(allt, t)
-        rank_ms = [round(float(v[0]), 3) for v in allt]
+    rank_ms = rank_diag = None
     launches = L.launch_count() - n0
-    clocks = sampler.stop() if sampler else None
+    clocks = sampler.stop()
+    if world > 1:
+        # per rank: device time per step, time inside the all-reduce bracket (transfer + waiting for the slowest rank: the
+        # rank that arrives last waits least) and its own GPU's median SM clock -- names the weak-scaling limiter
+        ar = sum(x.elapsed_time(y) for x, y in trainer.allreduce_events) / max(1, len(trainer.allreduce_events))
+        trainer.allreduce_events = None
+        mine = {'rank': rank, 'ms_per_step': round(ms_local / a.steps, 3), 'allreduce_bracket_ms': round(ar, 3),
+                'compute_ms': round(ms_local / a.steps - ar, 3), 'sm_mhz': (clocks or {}).get('sm_mhz'),
+                'reasons': (clocks or {}).get('reasons')}
+        allr = [None] * world
+        dist.all_gather_object(allr, mine, group=gloo)
+        rank_ms = [r['ms_per_step'] for r in allr]
+        rank_diag = allr
     ms_step = ms_total / a.steps
     value = world * B / (ms_step / 1e3)
     last_loss = float(loss.detach())
@@ -542,7 +550,7 @@ def run_b200(a, rank, local_rank, world):
                 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic', 'config': workload(a, world),
                 'clocks': clocks, 'e2e': e2e, 'gpu_launches': int(launches), 'roofline': roof,
                 'cpu_baseline': cpu, 'kernel_families_ms': fam, 'loss': last_loss,
-                'allreduce_ms': allreduce_ms, 'rank_ms_per_step': rank_ms, 'conv_sites_ms': sites,
+                'allreduce_ms': allreduce_ms, 'rank_ms_per_step': rank_ms, 'rank_diagnostics': rank_diag, 'conv_sites_ms': sites,
                 'input_pipeline': pipe,
                 'stock_cuda': stock,
                 'vs_stock_cuda': (value / stock['clips_s']) if stock and stock.get('clips_s') else None,

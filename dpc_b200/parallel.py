@@ -42,6 +42,7 @@ class FlatTrainer:
         self.lr, self.wd, self.betas, self.eps = lr, weight_decay, betas, eps
         self.step_count = 0
         self.group = process_group
+        self.allreduce_events = None      # set to [] to collect a (start, end) CUDA event pair per all-reduce (bench.py)
         self.world = dist.get_world_size(process_group) if (distributed and dist.is_available() and dist.is_initialized()) else 1
         if self.world > 1:
             # replicas start identical whatever each rank's RNG did (nn.DataParallel re-broadcasts rank 0's parameters
@@ -56,7 +57,14 @@ class FlatTrainer:
         if self.world > 1:
             from . import engine
             tok = engine._TIMER.start('allreduce') if engine._TIMER is not None else None
+            ev = None
+            if self.allreduce_events is not None:
+                ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+                ev[0].record()
             dist.all_reduce(self.flat_g, op=dist.ReduceOp.SUM, group=self.group)
+            if ev is not None:
+                ev[1].record()
+                self.allreduce_events.append(ev)
             if tok is not None:
                 engine._TIMER.stop(tok)
 

@@ -45,6 +45,8 @@ SITES = {
     'score_dfinf': ('score bwd: d(finf) = dS^T . pred (wgrad form)', 'tensor', 2 * M2 * M2 * 256, M2 * M2 * 4 + 2 * M2 * 256 * 4),
     'ce_fwd': ('NCE cross-entropy + top-k forward over the [6144,6144] score', 'hbm', 0, M2 * M2 * 4),
     'ce_bwd': ('NCE cross-entropy backward (softmax - onehot) -> d(score)', 'hbm', 0, 2 * M2 * M2 * 4),
+    'augment': ('input pipeline: 128 clips x 40 uint8 frames 200x150 -> block [128,8,3,5,128,128] fp32 (crop/resize/flip/grey/jitter/normalise)',
+                'hbm', 0, 128 * 40 * (150 * 200 * 3 + 3 * 128 * 128 * 4)),
 }
 KEYS = ['gpu__time_duration.sum', 'sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active',
         'smsp__issue_active.avg.pct_of_peak_sustained_active', 'sm__warps_active.avg.pct_of_peak_sustained_active',

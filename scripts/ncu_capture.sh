@@ -37,6 +37,8 @@ timeout 200 $N -k regex:conv_tc_kernel        -s 1  -c 1 -o gpurun_out/${TAG}_sc
 timeout 200 $N -k regex:wgrad_tc_kernel       -s 1  -c 1 -o gpurun_out/${TAG}_score_dfinf $S > /dev/null 2>&1
 timeout 200 $N -k regex:ce_fwd                -s 1  -c 1 -o gpurun_out/${TAG}_ce_fwd     $S > /dev/null 2>&1
 timeout 200 $N -k regex:ce_bwd                -s 1  -c 1 -o gpurun_out/${TAG}_ce_bwd     $S > /dev/null 2>&1
+# on-device input pipeline (config-2 batch)
+timeout 200 $N -k regex:augment_kernel        -s 3  -c 1 -o gpurun_out/${TAG}_augment    python scripts/bench_augment.py > /dev/null 2>&1
 # R34 @ 224^2, B = 44 (BASELINE configs 4 / 5): the 14x14 layer3 site (56 % of that network's FLOPs)
 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 4000 --csv --log-file gpurun_out/${TAG}_r34_launches.csv $R > gpurun_out/${TAG}_r34_l.log 2>&1
 timeout 300 $N -k regex:conv_tc_kernel        -s 4  -c 1 -o gpurun_out/${TAG}_r34_conv_l3 $R > /dev/null 2>&1
