@@ -23,38 +23,6 @@ from .resnet_2d3d import get_tensor
 _calls = itertools.count()
 
 
-def bn_buffers(backbone):
-    """{engine BN name: (running_mean, running_var)} of a track_running_stats=True backbone"""
-    out = {}
-    for name, mod in backbone.named_modules():
-        if isinstance(mod, nn.BatchNorm3d):
-            out[name] = (mod.running_mean, mod.running_var)
-    return out
-
-
-class _LcBackboneFn(torch.autograd.Function):
-    @staticmethod
-    def forward(ctx, x, network, names, need, training, bn_names, *tensors):
-        n = len(names)
-        P = dict(zip(names, tensors[:n]))
-        bufs = tensors[n:]
-        bn_state = {k: (bufs[2 * i], bufs[2 * i + 1]) for i, k in enumerate(bn_names)}
-        rows, dims, bctx = engine.backbone_forward(network, x, P, need_ctx=need, bn_state=bn_state, training=training)
-        ctx.bctx, ctx.names, ctx.nbuf = bctx, names, len(bufs)
-        ctx.save_for_backward(*tensors[:n])
-        return rows
-
-    @staticmethod
-    @once_differentiable
-    def backward(ctx, drows):
-        if ctx.bctx is None:
-            raise RuntimeError('backbone forward ran without saving activations')
-        P = dict(zip(ctx.names, ctx.saved_tensors))
-        G = engine.backbone_backward(ctx.bctx, drows.contiguous(), P)
-        ctx.bctx = None
-        return (None,) * 6 + tuple(G[n] for n in ctx.names) + (None,) * ctx.nbuf
-
-
 class _LcHeadFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, rows, dims, B, N, training, gru_p, fc_p, seed, need, rm, rv, *params):
@@ -105,19 +73,10 @@ class LC(nn.Module):
         (B, N, C, SL, H, W) = block.shape
         x = block.reshape(B * N, C, SL, H, W).contiguous().float()
         bb = self.backbone
-        params = [get_tensor(bb, n).contiguous() for n in bb._names]
-        bn_names = [k for k, m in bb.named_modules() if isinstance(m, nn.BatchNorm3d)]
-        bufs = []
-        for k in bn_names:
-            m = get_tensor(bb, k)
-            bufs += [m.running_mean, m.running_var]
         grad_on = torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
-        rows = _LcBackboneFn.apply(x, bb.network, bb._names, grad_on, self.training, bn_names, *params, *bufs)
+        rows, dims = bb.forward_rows(x)                              # running statistics handled by the backbone module
         if self.training:
-            for k in bn_names:
-                get_tensor(bb, k).num_batches_tracked += 1
             self.final_bn.num_batches_tracked += 1
-        dims = bb.out_dims(SL, H, W)
         if dims[0] != self.last_duration or dims[1] != self.last_size:
             raise ValueError('feature map %s does not match last_duration=%d / last_size=%d'
                              % (dims, self.last_duration, self.last_size))

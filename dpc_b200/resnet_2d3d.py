@@ -95,15 +95,21 @@ class Bottleneck2d(_Bottleneck):                                   # resnet_2d3d
 
 
 class _BackboneFn(torch.autograd.Function):
-    """x [NB,3,T,H,W] -> channels-last feature rows [NB*To*Ho*Wo, feature_size]"""
+    """x [NB,3,T,H,W] -> channels-last feature rows [NB*To*Ho*Wo, feature_size].
+    `tensors` = the parameters in `names` order, then (running_mean, running_var) per name in `bn_names` (empty for
+    track_running_stats=False).  With buffers: training -> batch statistics + momentum update of the buffers in place;
+    eval -> the buffers are the statistics (and the backward treats them as constants)."""
 
     @staticmethod
-    def forward(ctx, x, network, names, need, *params):
+    def forward(ctx, x, network, names, need, training, bn_names, *tensors):
         # `need` is decided by the caller: grad mode is always off inside Function.forward
-        P = dict(zip(names, params))
-        rows, dims, bctx = engine.backbone_forward(network, x, P, need_ctx=need)
-        ctx.bctx, ctx.names = bctx, names
-        ctx.save_for_backward(*params)
+        n = len(names)
+        P = dict(zip(names, tensors[:n]))
+        bufs = tensors[n:]
+        bn_state = {k: (bufs[2 * i], bufs[2 * i + 1]) for i, k in enumerate(bn_names)} if bn_names else None
+        rows, dims, bctx = engine.backbone_forward(network, x, P, need_ctx=need, bn_state=bn_state, training=training)
+        ctx.bctx, ctx.names, ctx.nbuf = bctx, names, len(bufs)
+        ctx.save_for_backward(*tensors[:n])
         return rows
 
     @staticmethod
@@ -114,7 +120,7 @@ class _BackboneFn(torch.autograd.Function):
         P = dict(zip(ctx.names, ctx.saved_tensors))
         G = engine.backbone_backward(ctx.bctx, drows.contiguous(), P)
         ctx.bctx = None
-        return (None, None, None, None) + tuple(G[n] for n in ctx.names)
+        return (None,) * 6 + tuple(G[n] for n in ctx.names) + (None,) * ctx.nbuf
 
 
 class ResNet2d3d_full(nn.Module):                                  # resnet_2d3d.py:205-270
@@ -185,8 +191,6 @@ class ResNet2d3d_full(nn.Module):                                  # resnet_2d3d
 
     def forward_rows(self, x):
         """x [NB,3,T,H,W] -> (rows [NB*To*Ho*Wo, feature_size] channels-last, (To,Ho,Wo))"""
-        if self.track_running_stats:
-            raise NotImplementedError('track_running_stats=True (eval/LC) is a SURVEY.md §8(f) "next" row')
         if x.dim() != 5 or x.shape[1] != 3:
             raise ValueError('expected [NB,3,T,H,W], got %s' % (tuple(x.shape),))
         if not x.is_cuda:
@@ -196,7 +200,16 @@ class ResNet2d3d_full(nn.Module):                                  # resnet_2d3d
         # copies as plain attributes, so named_parameters() is empty there
         params = [get_tensor(self, n).contiguous() for n in self._names]
         need = torch.is_grad_enabled() and any(p.requires_grad for p in params)
-        rows = _BackboneFn.apply(x, self.network, self._names, need, *params)
+        bn_names, bufs = (), []
+        if self.track_running_stats:                                # nn.BatchNorm3d default (resnet_2d3d.py:206): LC / eval
+            bn_names = tuple(k for k, m in self.named_modules() if isinstance(m, nn.BatchNorm3d))
+            for k in bn_names:
+                m = get_tensor(self, k)
+                bufs += [m.running_mean, m.running_var]
+        rows = _BackboneFn.apply(x, self.network, self._names, need, self.training, bn_names, *params, *bufs)
+        if self.track_running_stats and self.training:
+            for k in bn_names:
+                get_tensor(self, k).num_batches_tracked += 1
         return rows, self.out_dims(x.shape[2], x.shape[3], x.shape[4])
 
     def forward(self, x):                                           # resnet_2d3d.py:259-270

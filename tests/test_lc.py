@@ -148,3 +148,33 @@ def test_standalone_convgru_cell_forward():
     assert rel_err(out, O.gru_cell(x, h, sdo))[0] < 1e-4
     out0 = cell(x.cuda(), None)
     assert rel_err(out0, O.gru_cell(x, torch.zeros_like(h), sdo))[0] < 1e-4
+
+
+@pytest.mark.gpu
+def test_standalone_backbone_with_running_statistics():
+    """resnet18_2d3d_full() with the reference's default track_running_stats=True (backbone/resnet_2d3d.py:206), used
+    stand-alone: train mode = batch statistics (identical to the track_running_stats=False module) + buffer update;
+    eval mode = the buffers"""
+    from dpc_b200.resnet_2d3d import resnet18_2d3d_full
+    torch.manual_seed(3)
+    a = resnet18_2d3d_full().cuda()
+    b = resnet18_2d3d_full(track_running_stats=False).cuda()
+    b.load_state_dict({k: v for k, v in a.state_dict().items() if 'running' not in k and 'num_batches' not in k})
+    x = torch.randn(4, 3, 5, 64, 64, device='cuda')
+    a.train()
+    ya = a(x)
+    yb = b(x)
+    assert ya.shape == (4, 256, 2, 4, 4) and torch.equal(ya, yb)
+    assert int(a.bn1.num_batches_tracked) == 1 and int(a.layer4[1].bn2.num_batches_tracked) == 1
+    x64 = torch.nn.functional.conv3d(x.double(), a.conv1.weight.double(), None, (1, 2, 2), (0, 3, 3))
+    m = x64.mean((0, 2, 3, 4))
+    v = x64.var((0, 2, 3, 4), unbiased=True)
+    assert rel_err(a.bn1.running_mean, 0.1 * m.float())[0] < 1e-4
+    assert rel_err(a.bn1.running_var, (0.9 + 0.1 * v).float())[0] < 1e-4
+    ya.square().mean().backward()
+    assert a.conv1.weight.grad is not None and torch.isfinite(a.conv1.weight.grad).all()
+    a.eval()
+    with torch.no_grad():
+        ye = a(x)
+    assert torch.isfinite(ye).all() and not torch.equal(ye, ya)
+    assert int(a.bn1.num_batches_tracked) == 1
