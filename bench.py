@@ -531,7 +531,10 @@ def run_b200(a, rank, local_rank, world):
         barrier()
         if rank == 0:
             try:
-                stock = run_stock_cuda(a, world, steps=max(1, min(a.stock_steps, a.steps)))
+                # DataParallel steps cost seconds each (Python mask loops in every replica, serialised by the GIL): keep the
+                # multi-GPU leg short so that the whole line stays within minutes at N = 8
+                stock = run_stock_cuda(a, world, steps=max(1, min(a.stock_steps if world == 1 else 2, a.steps)),
+                                       warmup=2 if world == 1 else 1)
             except Exception as exc:                                 # report, never hide: the leg is evidence, not product
                 stock = {'error': '%s: %s' % (type(exc).__name__, str(exc)[:300])}
             torch.cuda.empty_cache()
