@@ -89,3 +89,58 @@ def test_full_batch_properties():
     if b is not None:
         px = u8[b, f // SL, :, f % SL].round()
         assert torch.equal(px[0], px[1]) and torch.equal(px[1], px[2])
+
+
+def _random_case(rng, recipe):
+    if recipe == 'ucf101':
+        W, H = rng.randint(224, 300), rng.randint(224, 280)
+        S = rng.choice([64, 96, 112, 128])
+    else:
+        S = rng.choice([32, 48, 64, 96, 128])
+        W, H = rng.randint(S // 2 + 8, 3 * S), rng.randint(S // 2 + 8, 3 * S)      # up- and down-scaling, any aspect
+    return W, H, S
+
+
+@pytest.mark.parametrize('recipe', ['k400', 'ucf101'])
+def test_random_geometries_match_oracle(recipe):
+    """randomised frame sizes / output sizes (up-scaling, strong down-scaling with wide tap windows, the Scale + CenterCrop
+    fallback for extreme aspect ratios, flips on both sides of the resize): every case bit-exact against the oracle"""
+    from dpc_b200 import augmentation as D
+    rng = random.Random(2024 if recipe == 'k400' else 2025)
+    for case in range(10 if recipe == 'k400' else 4):
+        W, H, S = _random_case(rng, recipe)
+        N, SL = 2, 2
+        frames = A.make_frames(900 + case, N * SL, H, W)
+        seed = 5000 + case
+        random.seed(seed)
+        np.random.seed(seed)
+        tr = D.ucf101_transform(S) if recipe == 'ucf101' else D.k400_transform(S)
+        got = tr(torch.from_numpy(frames).cuda(), N, SL)[0].cpu().numpy()
+        random.seed(seed)
+        np.random.seed(seed)
+        plan = (A.plan_ucf101 if recipe == 'ucf101' else A.plan_k400)(N * SL, W, H, S)
+        ref, _ = A.augment_clip(frames, plan, N, SL)
+        assert np.array_equal(got.view(np.uint32), ref.view(np.uint32)), (recipe, case, W, H, S, plan.box, plan.resize)
+
+
+def test_odd_output_size_and_bilinear_scale():
+    """an output whose pixel count is not a multiple of 4 (scalar store path) and Scale(..., BILINEAR)"""
+    from dpc_b200 import augmentation as D
+    W, H, N, SL = 90, 70, 1, 3
+    frames = A.make_frames(77, N * SL, H, W)
+    tr = D.Compose([D.RandomCrop(size=(50, 61)), D.Scale(size=(37, 29), interpolation=D.BILINEAR), D.RandomHorizontalFlip(),
+                    D.RandomGray(consistent=False, p=0.5), D.ColorJitter(0.4, 0.3, 0.2, 0.1), D.ToTensor(), D.Normalize()])
+    random.seed(31)
+    np.random.seed(31)
+    got = tr(torch.from_numpy(frames).cuda(), N, SL)[0].cpu().numpy()
+    random.seed(31)
+    np.random.seed(31)
+    plan = A.ClipPlan(N * SL, W, H)
+    A.plan_random_crop(plan, (50, 61))
+    plan.resize = ('bilinear', (37, 29))
+    A.plan_flip(plan)
+    A.plan_gray(plan)
+    A.plan_jitter(plan, 0.4, 0.3, 0.2, 0.1)
+    ref, _ = A.augment_clip(frames, plan, N, SL)
+    assert got.shape == (1, 3, 3, 29, 37)
+    assert np.array_equal(got.view(np.uint32), ref.view(np.uint32))
