@@ -27,6 +27,7 @@ def _st():
 
 def rel(a, b):
     a, b = a.double(), b.double()
+    a, b = a.detach(), b.detach()
     return float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
 
 
