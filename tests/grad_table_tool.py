@@ -1,7 +1,7 @@
 """DEV TOOL (test infrastructure, not product): end-to-end parameter-gradient error of the product path as the batch
 grows, against the oracle on the same GPU in fp64 -- with the fp32 oracle's own distance from fp64 beside it.
 
-    python scripts/grad_table.py [--out gpurun_out/r2_grad_table.json] [--max_b 128]
+    python tests/grad_table_tool.py [--out gpurun_out/r2_grad_table.json] [--max_b 128]
 
 Rows: 2d3d-R18, 128^2, eval mode (dropout off, BatchNorm batch statistics), B in {2, 8, 32, 128}, for two parameter sets:
   'reference-init'  the reference's own initialisation (oracle.reference_init_state_dict: kaiming fan_out / orthogonal /

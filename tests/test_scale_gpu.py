@@ -284,7 +284,7 @@ def _record(res):
 
 
 # End-to-end parameter gradients (rel-L2 against the fp32 oracle).  Measured on B200 (profiles/r2_grad_table.md, tool:
-# scripts/grad_table.py, fp64 oracle on the same GPU as the arbiter): the error does NOT fall with the batch -- it is the
+# tests/grad_table_tool.py, fp64 oracle on the same GPU as the arbiter): the error does NOT fall with the batch -- it is the
 # forward rounding level amplified ~100-300x by the network's conditioning (BatchNorm backward projections, the CE
 # softmax), for ANY arithmetic: the exact-fp32 oracle is 2-5e-3 from fp64 at every B in {2, 8, 32, 128}, this path
 # (3xBF16 operands, forward error 6-9e-5 vs the oracle's 8e-6) 0.8-1.5e-2 (worst tensor 1.1-2.0e-2), a constant ~4x ratio.
