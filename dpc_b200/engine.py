@@ -14,6 +14,7 @@ memory (caching allocator) and the current stream only; every FLOP below is issu
 libdpc_b200.so.
 """
 import math
+import os
 
 import torch
 
@@ -35,8 +36,10 @@ def set_timer(timer):
 class EventTimer:
     """CUDA-event timer on the current stream; .totals() -> {tag: (calls, ms)} after a synchronize"""
 
-    def __init__(self):
+    def __init__(self, keep_overlap=False):
         self.records = []
+        self.streams = []                 # cuda stream handle of every record (timeline diagnostics)
+        self.keep_overlap = keep_overlap  # True: the backward keeps its chain / side streams while being timed
 
     def start(self, tag, detail=None):
         a = torch.cuda.Event(enable_timing=True)
@@ -47,6 +50,7 @@ class EventTimer:
     def stop(self, tok):
         tok[2].record()
         self.records.append(tok)
+        self.streams.append(torch.cuda.current_stream().cuda_stream)
 
     def totals(self):
         torch.cuda.synchronize()
@@ -493,6 +497,32 @@ def _wgrad_async(site, x_op, dy_op, main, side):
     return dw
 
 
+# When the weight gradient of a site is launched.  'early' (DPC_WGRAD_DEFER=0): as soon as its dy planes exist, i.e.
+# concurrently with the dgrad of the same site -- two tensor-bound kernels that only take turns on the tensor pipe.
+# 'deferred' (default): after that dgrad has been enqueued, so the wgrad starts under the HBM-bound BatchNorm-backward passes
+# of the NEXT site.  Measured with scripts/timeline_step.py (B = 128, same box): 70.98 vs 71.91 ms/step.  Either way the
+# overlap buys little: kernels that share the GPU slow each other by 40-60 % (bn_bwd 10.6 -> 15.3 ms, dgrad 15.6 -> 23 ms under
+# 40 ms of concurrent wgrad) -- the step runs under `sw_power_cap` throughout, so concurrency trades clock for occupancy.
+WGRAD_DEFER = os.environ.get('DPC_WGRAD_DEFER', '1') != '0'
+
+
+class _WgradQueue:
+    def __init__(self, main, side):
+        self.main, self.side, self.q = main, side, []
+
+    def add(self, G, key, site, x_op, dy_op):
+        if self.side is None or not WGRAD_DEFER:
+            G[key] = _wgrad_async(site, x_op, dy_op, self.main, self.side)
+        else:
+            self.q.append((G, key, site, x_op, dy_op))
+
+    def flush(self):
+        """call after the dgrad that consumes the same dy has been enqueued on the chain stream"""
+        for G, key, site, x_op, dy_op in self.q:
+            G[key] = _wgrad_async(site, x_op, dy_op, self.main, self.side)
+        self.q.clear()
+
+
 _CHAIN_STREAMS = {}
 
 
@@ -507,7 +537,7 @@ def _chain_stream(device):
 
 def backbone_backward(ctx, dout, P):
     """dout: rows [NB*To*Ho*Wo, 256].  Returns dict name -> grad (parameter layouts)."""
-    if not (OVERLAP_WGRAD and _TIMER is None):
+    if not (OVERLAP_WGRAD and (_TIMER is None or _TIMER.keep_overlap)):
         return _backbone_backward(ctx, dout, P, None)
     caller = torch.cuda.current_stream()
     chain = _chain_stream(dout.device)
@@ -547,6 +577,7 @@ def _backbone_backward(ctx, dout, P, side):
     L = lib()
     st = _stream()
     main = torch.cuda.current_stream()
+    wq = _WgradQueue(main, side)
     G = {}
     blocks = ctx['blocks']
     ws_out = None          # BN-backward sums of this block's bn2, if the dgrad that produced `dout` fused them
@@ -573,30 +604,34 @@ def _backbone_backward(ctx, dout, P, side):
                     cd.rows_out, cd.Co, st, out_hi=rec['out_hi'], **kw)
                 dyd = op(dydr, dydp)
             del dout
-            G[p + '.conv3.weight'] = _wgrad_async(c3, rec['a2_op'], dy3, main, side)
+            wq.add(G, p + '.conv3.weight', c3, rec['a2_op'], dy3)
             da2 = c3.dgrad(dy3, st)
+            wq.flush()
             del dy3, dy3r, dy3p
             dy2r, dy2p, G[p + '.bn2.weight'], G[p + '.bn2.bias'], _ = _bn_bwd(
                 da2, rec['a2'], True, rec['y2'], rec['m2'], rec['r2'], P[p + '.bn2.weight'],
                 c2.rows_out, c2.Co, st, out_hi=(rec['a2_op'][0] if tc else None), **kw)
             dy2 = op(dy2r, dy2p)
             del da2
-            G[p + '.conv2.weight'] = _wgrad_async(c2, rec['a1_op'], dy2, main, side)
+            wq.add(G, p + '.conv2.weight', c2, rec['a1_op'], dy2)
             da1 = c2.dgrad(dy2, st)
+            wq.flush()
             del dy2, dy2r, dy2p
             dy1r, dy1p, G[p + '.bn1.weight'], G[p + '.bn1.bias'], _ = _bn_bwd(
                 da1, rec['a1'], True, rec['y1'], rec['m1'], rec['r1'], P[p + '.bn1.weight'],
                 c1.rows_out, c1.Co, st, out_hi=(rec['a1_op'][0] if tc else None), **kw)
             dy1 = op(dy1r, dy1p)
             del da1
-            G[p + '.conv1.weight'] = _wgrad_async(c1, rec['xin_op'], dy1, main, side)
+            wq.add(G, p + '.conv1.weight', c1, rec['xin_op'], dy1)
             if has_ds:
                 dx = c1.dgrad(dy1, st)
                 cd.dgrad(dyd, st, dx=dx)
-                G[p + '.downsample.0.weight'] = _wgrad_async(cd, rec['xin_op'], dyd, main, side)
+                wq.add(G, p + '.downsample.0.weight', cd, rec['xin_op'], dyd)
+                wq.flush()
                 del dyd, dydr, dydp
             else:
                 dx = c1.dgrad(dy1, st, dx=g)          # dx = g + dgrad
+                wq.flush()
             del dy1, dy1r, dy1p
             dout = dx
             rec.clear()
@@ -613,24 +648,27 @@ def _backbone_backward(ctx, dout, P, side):
                 cd.rows_out, cd.Co, st, out_hi=rec['out_hi'], **kw)
             dyd = op(dydr, dydp)
         del dout
-        G[p + '.conv2.weight'] = _wgrad_async(c2, rec['a1_op'], dy2, main, side)
+        wq.add(G, p + '.conv2.weight', c2, rec['a1_op'], dy2)
         # conv2 is always stride 1: its dgrad also reduces bn1's backward sums in the epilogue (FUSE_BN_REDUCE)
         ws1 = None
         if tc and c2.fuse_bnred:
             da1, ws1 = c2.dgrad_bnred(dy2, st, rec['a1_op'][0], rec['y1'], rec['m1'], rec['r1'])
+            wq.flush()
         else:
             da1 = c2.dgrad(dy2, st)
+            wq.flush()
         del dy2, dy2r, dy2p
         dy1r, dy1p, G[p + '.bn1.weight'], G[p + '.bn1.bias'], _ = _bn_bwd(
             da1, rec['a1'], True, rec['y1'], rec['m1'], rec['r1'], P[p + '.bn1.weight'],
             c1.rows_out, c1.Co, st, out_hi=(rec['a1_op'][0] if tc else None), ws=ws1, **kw)
         dy1 = op(dy1r, dy1p)
         del da1
-        G[p + '.conv1.weight'] = _wgrad_async(c1, rec['xin_op'], dy1, main, side)
+        wq.add(G, p + '.conv1.weight', c1, rec['xin_op'], dy1)
         if has_ds:
             dx = c1.dgrad(dy1, st)
             cd.dgrad(dyd, st, dx=dx)
-            G[p + '.downsample.0.weight'] = _wgrad_async(cd, rec['xin_op'], dyd, main, side)
+            wq.add(G, p + '.downsample.0.weight', cd, rec['xin_op'], dyd)
+            wq.flush()
             del dyd, dydr, dydp
         elif tc and c1.fuse_bnred and bi > 0 and blocks[bi - 1].get('out_hi') is not None \
                 and blocks[bi - 1]['spec']['block'] == 'basic':
@@ -638,8 +676,10 @@ def _backbone_backward(ctx, dout, P, side):
             prev = blocks[bi - 1]
             dx, ws_out = c1.dgrad_bnred(dy1, st, prev['out_hi'] if prev['spec']['final_relu'] else None,
                                         prev['y2'], prev['m2'], prev['r2'], dx=g)
+            wq.flush()
         else:
             dx = c1.dgrad(dy1, st, dx=g)          # dx = g + dgrad
+            wq.flush()
         del dy1, dy1r, dy1p
         dout = dx
         rec.clear()
@@ -677,6 +717,7 @@ def _backbone_backward(ctx, dout, P, side):
         dw0 = _stem_backward_unpooled(L, st, ctx, dout, P, G)
         del dout
     G['conv1.weight'] = dw0
+    wq.flush()
     if side is not None:
         main.wait_stream(side)
     return G
