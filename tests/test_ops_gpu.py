@@ -279,7 +279,7 @@ def test_nce_mask_and_ce(B, P, SQ):
         ref_loss = F.cross_entropy(score, target)
         ref_loss.backward()
         out, lse = E.nce_ce_forward(score.detach())
-        assert abs(float(out[0]) - float(ref_loss)) < 1e-5 * max(1.0, abs(float(ref_loss)))
+        assert abs(float(out[0]) - float(ref_loss.detach())) < 1e-5 * max(1.0, abs(float(ref_loss.detach())))
         tk = O.topk_accuracy(score.detach(), target)
         for i in range(3):
             assert abs(float(out[1 + i]) - float(tk[i])) < 1e-6
