@@ -144,3 +144,22 @@ def test_odd_output_size_and_bilinear_scale():
     ref, _ = A.augment_clip(frames, plan, N, SL)
     assert got.shape == (1, 3, 3, 29, 37)
     assert np.array_equal(got.view(np.uint32), ref.view(np.uint32))
+
+
+@pytest.mark.parametrize('hue', [-0.25, 0.1037, 0.5])
+def test_hue_rotation_all_colours(hue):
+    """every one of the 2^24 RGB colours through the kernel's HSV round trip (1024 frames of 128 x 128, identity geometry,
+    hue as the only jitter operation) against the oracle -- which tests/test_aug_oracle.py pins against Pillow on the same
+    exhaustive cube"""
+    from dpc_b200 import augmentation as D
+    r = np.arange(256, dtype=np.uint8)
+    cube = np.stack(np.meshgrid(r, r, r, indexing='ij'), -1).reshape(1024, 128, 128, 3)
+    tr = D.Compose([D.ColorJitter(hue=(hue, hue), p=1.0), D.ToTensor(), D.Normalize()])
+    got = tr(torch.from_numpy(cube).cuda(), 1024, 1)
+    torch.cuda.synchronize()
+    ref = A.adjust(cube.reshape(4096, 4096, 3), A.OP_HUE, hue).reshape(1024, 128, 128, 3)
+    lut = A.normalize(np.arange(256, dtype=np.uint8).reshape(256, 1, 1).repeat(3, -1))[..., 0]     # [3, 256] bytes -> floats
+    want = np.stack([lut[c][ref[..., c]] for c in range(3)], 1)                                   # [1024, 3, 128, 128]
+    g = got[0, :, :, 0].cpu().numpy()                                                             # [1024, 3, 128, 128]
+    bad = np.argwhere(g.view(np.uint32) != want.view(np.uint32))
+    assert len(bad) == 0, (len(bad), bad[:3].tolist())
