@@ -320,6 +320,8 @@ def run_b200(a, rank, local_rank, world):
     barrier()
     sampler = ClockSampler(local_rank)                                # every rank samples its own GPU
     trainer.allreduce_events = [] if world > 1 else None
+    allreduce_impl = None if world == 1 else ('dpc_flat_allreduce (library-owned NCCL communicator, compute stream)'
+                                              if trainer.comm is not None else 'torch.distributed.all_reduce')
     n0 = L.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -523,6 +525,7 @@ def run_b200(a, rank, local_rank, world):
     stock = None
     if not a.no_stock:
         import gc
+        trainer.close()
         del model, trainer, crit, x_dev, step
         if not a.no_e2e:
             del bufs
@@ -553,13 +556,15 @@ def run_b200(a, rank, local_rank, world):
                 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic', 'config': workload(a, world),
                 'clocks': clocks, 'e2e': e2e, 'gpu_launches': int(launches), 'roofline': roof,
                 'cpu_baseline': cpu, 'kernel_families_ms': fam, 'loss': last_loss,
-                'allreduce_ms': allreduce_ms, 'rank_ms_per_step': rank_ms, 'rank_diagnostics': rank_diag, 'conv_sites_ms': sites,
+                'allreduce_impl': allreduce_impl, 'allreduce_ms': allreduce_ms, 'rank_ms_per_step': rank_ms, 'rank_diagnostics': rank_diag, 'conv_sites_ms': sites,
                 'input_pipeline': pipe,
                 'stock_cuda': stock,
                 'vs_stock_cuda': (value / stock['clips_s']) if stock and stock.get('clips_s') else None,
                 'vs_stock_cuda_ideal_ddp': (value / stock['ideal_ddp_clips_s']) if stock and stock.get('ideal_ddp_clips_s') else None}
         print(json.dumps(line))
     if world > 1:
+        if a.no_stock:
+            trainer.close()
         dist.destroy_process_group()
 
 

@@ -75,6 +75,10 @@ _SIGS = {
     'dpc_relu_pool_bwd': (c_int, [P, P, P, c_int, c_int, c_int64, P]),
     'dpc_dropout_fwd': (c_int, [P, P, P, c_float, c_uint64, c_uint64, c_int64, P]),
     'dpc_mul': (c_int, [P, P, P, c_int64, P]),
+    'dpc_comm_unique_id': (c_int, [P]),
+    'dpc_comm_init': (c_int, [P, c_int, c_int, P]),
+    'dpc_flat_allreduce': (c_int, [P, P, c_int64, P]),
+    'dpc_comm_destroy': (c_int, [P]),
     'dpc_augment_clips': (c_int, [P, P, P, P, P, P] + [c_int] * 9 + [P]),
     'dpc_adam_step': (c_int, [P, P, P, P, c_int64, c_float, c_float, c_float, c_float, c_float, c_int, c_float, P]),
 }

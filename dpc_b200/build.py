@@ -46,7 +46,7 @@ def build(force=False, verbose=False):
             sys.stderr.write(out)
         if p.returncode:
             raise RuntimeError('nvcc failed: ' + ' '.join(cmd))
-    cmd = [NVCC, '-shared', '-o', LIB] + objs + ['-lcuda']
+    cmd = [NVCC, '-shared', '-o', LIB] + objs + ['-lcuda', '-ldl']
     subprocess.check_call(cmd)
     return LIB
 

@@ -5,7 +5,15 @@ collective (score matrix, BN statistics, mask and loss stay per rank -- the refe
 nn.DataParallel semantics, /root/reference/dpc/main.py:65,180,212).  The only exchange is ONE
 all-reduce (sum) of the flat fp32 gradient buffer over NCCL / NVLink, followed by a fused Adam
 (torch.optim.Adam(lr, weight_decay) semantics, main.py:81) that folds the 1/world scaling in.
+
+The all-reduce is issued by the library itself (`dpc_flat_allreduce`, csrc/comm.cu) on the compute stream, on a
+communicator whose unique id travels through torch.distributed (the plumbing: rendezvous, the initial parameter
+broadcast, barriers).  DPC_DIRECT_NCCL=0, a process sub-group, or a non-NCCL backend fall back to
+`torch.distributed.all_reduce`.
 """
+import ctypes
+import os
+
 import torch
 import torch.distributed as dist
 
@@ -49,6 +57,29 @@ class FlatTrainer:
             # every forward, main.py:65; one process per GPU needs it once)
             src = dist.get_global_rank(process_group, 0) if process_group is not None else 0
             dist.broadcast(self.flat_p, src=src, group=process_group)
+        self.comm = None
+        if (self.world > 1 and process_group is None and dist.get_backend() == 'nccl'
+                and os.environ.get('DPC_DIRECT_NCCL', '1') != '0'):
+            self._init_comm(dev)
+
+    def _init_comm(self, dev):
+        """the library's own NCCL communicator: rank 0 draws the unique id, torch.distributed carries it"""
+        rank = dist.get_rank()
+        ident = ctypes.create_string_buffer(128)
+        if rank == 0:
+            lib().comm_unique_id(ctypes.addressof(ident))
+        box = [ident.raw]
+        dist.broadcast_object_list(box, src=0)
+        ident = ctypes.create_string_buffer(box[0], 128)
+        comm = ctypes.c_void_p()
+        with torch.cuda.device(dev):
+            lib().comm_init(ctypes.addressof(ident), rank, self.world, ctypes.addressof(comm))
+        self.comm = comm.value
+
+    def close(self):
+        if getattr(self, 'comm', None):
+            lib().comm_destroy(self.comm)
+            self.comm = None
 
     def zero_grad(self):
         self.flat_g.zero_()
@@ -61,7 +92,10 @@ class FlatTrainer:
             if self.allreduce_events is not None:
                 ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
                 ev[0].record()
-            dist.all_reduce(self.flat_g, op=dist.ReduceOp.SUM, group=self.group)
+            if self.comm is not None:
+                lib().flat_allreduce(self.comm, ptr(self.flat_g), self.n, torch.cuda.current_stream().cuda_stream)
+            else:
+                dist.all_reduce(self.flat_g, op=dist.ReduceOp.SUM, group=self.group)
             if ev is not None:
                 ev[1].record()
                 self.allreduce_events.append(ev)

@@ -263,6 +263,17 @@ int dpc_mul(const float* a, const float* b, float* out, int64_t n, void* stream)
 int dpc_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1,
                   float beta2, float eps, float wd, int step, float gscale, void* stream);
 
+/* ---- data-parallel exchange (comm.cu) -------------------------------------------------------
+ * ONE all-reduce (sum, in place) of the flat fp32 gradient buffer over NCCL on the caller's stream: the gradient reduction
+ * of nn.DataParallel's backward (dpc/main.py:65,230) in the one-process-per-GPU layout.  NCCL is taken from the libnccl.so.2
+ * already loaded into the process.  dpc_comm_unique_id: rank 0 fills 128 bytes that the host distributes to every rank;
+ * dpc_comm_init: collective over all ranks (current CUDA device = this rank's GPU) -> opaque communicator. */
+#define DPC_COMM_ID_BYTES 128
+int dpc_comm_unique_id(void* id128 /*host, DPC_COMM_ID_BYTES*/);
+int dpc_comm_init(const void* id128 /*host*/, int rank, int world, void** comm);
+int dpc_flat_allreduce(void* comm, float* buf, int64_t n, void* stream);
+int dpc_comm_destroy(void* comm);
+
 /* ---- on-device clip augmentation (augment.cu): decoded uint8 frames -> the float32 block DPC_RNN.forward consumes --------
  * replaces the CPU transform chain utils/augmentation.py:147-384 composed as dpc/main.py:115-133 (RandomSizedCrop | RandomCrop +
  * Scale, RandomHorizontalFlip, RandomGray, ColorJitter, ToTensor, Normalize) and the reshuffle of dpc/dataset_3d.py:108-112,

@@ -71,10 +71,11 @@ def main():
         upd_s = (tr2.flat_p - p0).double()
         rel = float((upd_d - upd_s).norm() / upd_s.norm())
         grel = float((g_dist.double() - tr2.flat_g.double()).norm() / tr2.flat_g.double().norm())
-        res = dict(world=world, same_init=bool(same_init), same_after=bool(same_after), grad_rel_l2=grel, update_rel_l2=rel,
+        res = dict(world=world, direct_nccl=tr.comm is not None, same_init=bool(same_init), same_after=bool(same_after), grad_rel_l2=grel, update_rel_l2=rel,
                    update_norm=float(upd_s.norm()), loss=float(loss))
         print('MPRESULT ' + json.dumps(res), flush=True)
     dist.barrier()
+    tr.close()
     dist.destroy_process_group()
 
 

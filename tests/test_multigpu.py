@@ -13,18 +13,23 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
+@pytest.mark.parametrize('direct', [1, 0], ids=['library-allreduce', 'torch-allreduce'])
 @pytest.mark.parametrize('world', [2])
-def test_nccl_data_parallel_step_matches_single_process(world):
+def test_nccl_data_parallel_step_matches_single_process(world, direct):
+    """direct = 1: the all-reduce is dpc_flat_allreduce (csrc/comm.cu) on the library's own communicator; 0: the
+    torch.distributed fallback"""
     if torch.cuda.device_count() < world:
         pytest.skip('needs %d GPUs' % world)
+    env = dict(os.environ, DPC_DIRECT_NCCL=str(direct))
     cmd = [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node', str(world),
            '--master-addr', '127.0.0.1', '--master-port', '29631', os.path.join(ROOT, 'tests', 'mp_worker.py')]
-    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT, env=env)
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
     line = [l for l in out.stdout.splitlines() if l.startswith('MPRESULT ')]
     assert line, out.stdout[-2000:]
     res = json.loads(line[-1][len('MPRESULT '):])
     print(res)
+    assert res['direct_nccl'] == bool(direct)
     assert res['same_init'], 'FlatTrainer did not broadcast rank 0\'s parameters'
     assert res['same_after'], 'parameters differ across ranks after the step'
     # the all-reduced gradient equals the single-process sum of the two shards' gradients up to the summation order of the
