@@ -87,12 +87,28 @@ def measured_peaks():
 
 # ---------------------------------------------------------------------------------------------
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region"""
+    """SM clock / clock-event reasons of ONE GPU sampled every 100 ms during the timed region: in-process through NVML
+    (pynvml; no child process, so every rank can watch its own GPU), else an `nvidia-smi -lms 200` child"""
     Q = ('clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
          'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+    BITS = (('hw_slowdown', 0x8), ('hw_thermal_slowdown', 0x40), ('sw_thermal_slowdown', 0x20), ('sw_power_cap', 0x4))
 
     def __init__(self, index):
-        self.lines, self.proc = [], None
+        self.lines, self.proc, self.nv = [], None, None
+        self._stop = threading.Event()
+        try:
+            import pynvml
+            import torch
+            pynvml.nvmlInit()
+            uuid = 'GPU-' + str(torch.cuda.get_device_properties(index).uuid)
+            self.h = pynvml.nvmlDeviceGetHandleByUUID(uuid.encode() if hasattr(uuid, 'encode') else uuid)
+            self.mx = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.nv = pynvml
+            self.t = threading.Thread(target=self._poll, daemon=True)
+            self.t.start()
+            return
+        except Exception:
+            self.nv = None
         try:
             self.proc = subprocess.Popen(['nvidia-smi', '-i', str(index), '--query-gpu=' + self.Q,
                                           '--format=csv,noheader,nounits', '-lms', '200'],
@@ -102,18 +118,34 @@ class ClockSampler:
         except Exception:
             self.proc = None
 
+    def _poll(self):
+        nv = self.nv
+        get_reasons = getattr(nv, 'nvmlDeviceGetCurrentClocksEventReasons', None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+        while not self._stop.is_set():
+            try:
+                sm = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
+                r = int(get_reasons(self.h))
+                self.lines.append(', '.join([str(sm), str(self.mx)] + ['Active' if r & bit else 'Not Active' for _, bit in self.BITS]))
+            except Exception:
+                pass
+            self._stop.wait(0.1)
+
     def _read(self):
         for ln in self.proc.stdout:
             self.lines.append(ln.strip())
 
     def stop(self):
-        if self.proc is None:
+        if self.nv is not None:
+            self._stop.set()
+            self.t.join(timeout=2)
+        elif self.proc is not None:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)
+            except Exception:
+                self.proc.kill()
+        else:
             return None
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=5)
-        except Exception:
-            self.proc.kill()
         sm, mx, reasons = [], [], set()
         names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
         for ln in self.lines:
