@@ -145,3 +145,22 @@ def test_jitter_steps_and_normalise_match_torchvision():
         assert np.array_equal(np.array(F.adjust_hue(pim, f)), A.adjust(img, A.OP_HUE, f))
     x = F.normalize(F.to_tensor(pim), A.MEAN, A.STD).numpy()
     assert np.array_equal(x.view(np.uint32), A.normalize(img).view(np.uint32))
+
+
+def test_vectorised_tables_match_scalar_restatement_over_random_sizes():
+    """dpc_b200.augmentation._bilinear_table / _nearest_table (numpy-vectorised, what the product uploads) against the oracle's
+    scalar restatement of Pillow's coefficient code over 400 random (input, output) sizes incl. extreme ratios"""
+    from dpc_b200 import augmentation as D
+    rng = random.Random(77)
+    sizes = [(rng.randint(1, 700), rng.randint(1, 260)) for _ in range(380)] + [(1, 1), (1, 64), (700, 1), (256, 256), (2, 255),
+                                                                                 (1000, 8), (17, 224), (224, 17)] + \
+            [(n, n + d) for n in (31, 64, 127) for d in (-1, 1)] + [(rng.randint(200, 400), 128) for _ in range(6)]
+    for n_in, n_out in sizes:
+        xs, xc, xk = A.resample_coeffs(n_in, n_out)
+        ps, pc, pk = D._bilinear_table(n_in, n_out)
+        assert np.array_equal(ps, xs) and np.array_equal(pc, xc), (n_in, n_out)
+        assert pk.shape == xk.shape and np.array_equal(pk.astype(np.int64), xk), (n_in, n_out)
+        assert int(pk.sum(1).min()) > 0 and abs(int(pk.sum(1).max()) - (1 << 22)) <= pk.shape[1]      # weights sum to ~1.0
+        ns, nc, nk = A.nearest_coeffs(n_in, n_out)
+        qs, qc, qk = D._nearest_table(n_in, n_out)
+        assert np.array_equal(qs, ns) and np.array_equal(qc, nc) and np.array_equal(qk.astype(np.int64), nk), (n_in, n_out)
